@@ -1,0 +1,239 @@
+"""Scalar-semantics fp32 restatement (numpy) of the YOLO-LP post-processing path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Every function cites the
+reference lines (relative to ``/root/reference``) it restates.  All arithmetic
+is carried out in ``np.float32`` with the reference's association order and no
+fused multiply-add, because kept-set parity is defined bit-for-bit.
+
+Parity pin: ``tests/golden/*.npz`` (made by ``tests/golden/make_golden.py`` from
+the imported reference + torchvision 0.26.0 CPU).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+f32 = np.float32
+
+#: column groups of the 290-wide head row: province, alphabet, six characters
+#: (``yolov6/utils/nms.py:81-88``).
+GROUPS = ((13, 44), (44, 68), (68, 105), (105, 142), (142, 179), (179, 216), (216, 253), (253, 290))
+ROW = 290
+OUT = 28
+MAX_NMS = 30000  # yolov6/utils/nms.py:62
+
+
+# --------------------------------------------------------------------------- geometry
+def generate_anchors_eval(level_hw, strides, grid_cell_offset=0.5):
+    """``generate_anchors(..., is_eval=True, mode='af')``,
+    ``yolov6/assigners/anchor_generator.py:11-31``.
+
+    level_hw: [(h, w), ...].  Returns (anchor_points[A,2], stride_tensor[A,1]),
+    level-major, row-major inside a level, points = (x+off, y+off) in grid units.
+    """
+    pts, strs = [], []
+    for (h, w), s in zip(level_hw, strides):
+        sx = np.arange(w, dtype=np.int64).astype(f32) + f32(grid_cell_offset)
+        sy = np.arange(h, dtype=np.int64).astype(f32) + f32(grid_cell_offset)
+        yy, xx = np.meshgrid(sy, sx, indexing="ij")
+        pts.append(np.stack([xx, yy], -1).reshape(-1, 2).astype(f32))
+        strs.append(np.full((h * w, 1), s, dtype=f32))
+    return np.concatenate(pts, 0), np.concatenate(strs, 0)
+
+
+def dist2bbox(distance, anchor_points, box_format="xyxy"):
+    """``yolov6/utils/general.py:29-40``."""
+    distance = np.asarray(distance, f32)
+    lt, rb = distance[..., :2], distance[..., 2:4]
+    x1y1 = (anchor_points - lt).astype(f32)
+    x2y2 = (anchor_points + rb).astype(f32)
+    if box_format == "xyxy":
+        return np.concatenate([x1y1, x2y2], -1)
+    if box_format == "xywh":
+        c_xy = ((x1y1 + x2y2).astype(f32) / f32(2)).astype(f32)
+        wh = (x2y2 - x1y1).astype(f32)
+        return np.concatenate([c_xy, wh], -1)
+    raise ValueError(box_format)
+
+
+def dist2cor(distance, anchor_points):
+    """``yolov6/utils/general.py:51-66``: 8 distances -> TL, BL, BR, TR corners."""
+    d = np.asarray(distance, f32)
+    ax, ay = anchor_points[..., 0], anchor_points[..., 1]
+    out = np.stack(
+        [ax - d[..., 0], ay - d[..., 1],   # TL = a - lt
+         ax - d[..., 2], ay + d[..., 3],   # BL
+         ax + d[..., 4], ay + d[..., 5],   # BR = a + rb
+         ax + d[..., 6], ay - d[..., 7]],  # TR
+        -1)
+    return out.astype(f32)
+
+
+def sigmoid(x):
+    """torch.sigmoid in fp32.  Not bit-reproducible across libms; parity for
+    this one op is held to 1e-5 relative (north_star)."""
+    x = np.asarray(x, f32)
+    return (f32(1) / (f32(1) + np.exp(-x, dtype=f32))).astype(f32)
+
+
+CLS_NAMES = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5")
+
+
+def detect_decode(levels, strides):
+    """Eval tail of ``Detect.forward``, ``yolov6/models/effidehead.py:247-301``
+    (``use_dfl=False``): everything after the prediction convs.
+
+    levels: list (per FPN level) of dicts with raw conv outputs, NCHW fp32:
+    ``pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w] reg[B,4,h,w] cor[B,8,h,w]``.
+    Returns ``[B, A, 290]``.
+    """
+    hw = [lv["reg"].shape[2:] for lv in levels]
+    ap, st = generate_anchors_eval(hw, strides)
+    B = levels[0]["reg"].shape[0]
+
+    def flat(name):  # effidehead.py:260-280  reshape [B,C,hw] -> cat levels -> permute
+        return np.concatenate([lv[name].reshape(B, lv[name].shape[1], -1) for lv in levels], -1).transpose(0, 2, 1)
+
+    box = dist2bbox(flat("reg"), ap[None], "xywh")          # :283
+    cor = dist2cor(flat("cor"), ap[None])                     # :284
+    box = (box * st[None]).astype(f32)                        # :285
+    cor = (cor * st[None]).astype(f32)                        # :286
+    cls = [sigmoid(flat(n)) for n in CLS_NAMES]               # :251-258
+    ones = np.ones((B, box.shape[1], 1), f32)                 # :290
+    return np.concatenate([box, ones, cor] + cls, -1).astype(f32)   # :287-301
+
+
+# --------------------------------------------------------------------------- NMS path
+def xywh2xyxy(x):
+    """``yolov6/utils/nms.py:21-28``."""
+    x = np.asarray(x, f32)
+    h0 = (x[:, 2] / f32(2)).astype(f32)
+    h1 = (x[:, 3] / f32(2)).astype(f32)
+    return np.stack([x[:, 0] - h0, x[:, 1] - h1, x[:, 0] + h0, x[:, 1] + h1], 1).astype(f32)
+
+
+def _sum8(c, last):
+    """Left-to-right fp32 sum of seven group confidences plus column ``last``."""
+    s = (c[:, 0] + c[:, 1]).astype(f32)
+    for k in (2, 3, 4, 5, 6):
+        s = (s + c[:, k]).astype(f32)
+    return (s + c[:, last]).astype(f32)
+
+
+def score_rows(x):
+    """``nms.py:76-97`` for one image ``x[A,290]``: returns (det[A,28], filter_mean[A]).
+
+    filter_mean reproduces the reference's bug of adding ``ad4_conf`` twice and
+    never ``ad5_conf`` (``nms.py:90-91``).
+    """
+    x = np.asarray(x, f32)
+    cls = (x[:, 13:] * x[:, 4:5]).astype(f32)                                   # :76
+    box = xywh2xyxy(x[:, :4])                                                   # :79
+    conf = np.stack([cls[:, s - 13:e - 13].max(1) for s, e in GROUPS], 1)       # :81-88
+    arg = np.stack([cls[:, s - 13:e - 13].argmax(1) for s, e in GROUPS], 1)     # first index on ties
+    filt = (_sum8(conf, 6) / f32(8)).astype(f32)                                # :90-91
+    det = np.concatenate([box, x[:, 5:13], conf, arg.astype(f32)], 1).astype(f32)  # :94-96
+    return det, filt
+
+
+def nms_score(det):
+    """``nms.py:120``: mean of all eight group confidences, left to right."""
+    return (_sum8(det[:, 12:20], 7) / f32(8)).astype(f32)
+
+
+def greedy_nms(boxes, scores, iou_thres, limit=None):
+    """``torchvision.ops.nms`` CPU kernel (0.26.0), call site ``nms.py:121``.
+
+    Stable descending sort; areas precomputed in fp32; fp32 IoU with the union
+    associated as ``(area_i + area_j) - inter``; suppression iff
+    ``(double)iou > iou_thres``.  ``limit`` stops after that many keeps (legal:
+    the reference truncates afterwards, ``nms.py:122-123``).
+    """
+    boxes = np.asarray(boxes, f32)
+    scores = np.asarray(scores, f32)
+    n = boxes.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int64)
+    order = np.argsort(-scores.astype(np.float64), kind="stable")
+    x1, y1, x2, y2 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
+    area = ((x2 - x1).astype(f32) * (y2 - y1).astype(f32)).astype(f32)
+    supp = np.zeros(n, bool)
+    keep = []
+    thr = float(iou_thres)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for k, i in enumerate(order):
+            if supp[i]:
+                continue
+            keep.append(i)
+            if limit is not None and len(keep) >= limit:
+                break
+            r = order[k + 1:]
+            w = np.maximum(f32(0), (np.minimum(x2[i], x2[r]) - np.maximum(x1[i], x1[r])).astype(f32))
+            h = np.maximum(f32(0), (np.minimum(y2[i], y2[r]) - np.maximum(y1[i], y1[r])).astype(f32))
+            inter = (w * h).astype(f32)
+            ovr = (inter / ((area[i] + area[r]).astype(f32) - inter).astype(f32)).astype(f32)
+            supp[r[ovr.astype(np.float64) > thr]] = True
+    return np.asarray(keep, np.int64)
+
+
+def nms_one_image(x, conf_thres, iou_thres, max_det=300, max_nms=MAX_NMS):
+    """Loop body of ``non_max_suppression``, ``nms.py:68-125``, for one image.
+
+    Returns (rows[k,28], anchor_index[k]).  When more than ``max_nms`` rows pass
+    the filter the reference takes an *unstable* argsort (``nms.py:115-116``), so
+    its result is implementation-defined on ties; the oracle (and the product)
+    define the cut as (score descending, anchor ascending).
+    """
+    det, filt = score_rows(x)
+    mask = filt >= f32(conf_thres)
+    idx = np.nonzero(mask)[0]
+    det = det[mask]                                                             # :97
+    if det.shape[0] == 0:
+        return np.zeros((0, OUT), f32), np.zeros((0,), np.int64)
+    score = nms_score(det)
+    if det.shape[0] > max_nms:                                                  # :115-116
+        o = np.argsort(-score.astype(np.float64), kind="stable")[:max_nms]
+        det, idx, score = det[o], idx[o], score[o]
+    keep = greedy_nms(det[:, :4], score, iou_thres, limit=max_det)[:max_det]    # :121-123
+    return det[keep], idx[keep]
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None,
+                        agnostic=False, multi_label=False, max_det=300, return_index=False):
+    """``yolov6/utils/nms.py:31-130``.  ``classes``/``agnostic``/``multi_label``
+    are accepted and ignored exactly as in the reference; the 10 s wall-clock
+    ``time_limit`` (``:126-128``) is deliberately not reproduced; the input is
+    not mutated (the reference's ``x[:,13:] *= x[:,4:5]`` side effect, ``:76``)."""
+    assert 0 <= conf_thres <= 1, f"conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided."
+    assert 0 <= iou_thres <= 1, f"iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided."
+    prediction = np.asarray(prediction, f32)
+    rows, idxs = [], []
+    for x in prediction:
+        r, i = nms_one_image(x, conf_thres, iou_thres, max_det)
+        rows.append(r)
+        idxs.append(i)
+    return (rows, idxs) if return_index else rows
+
+
+# --------------------------------------------------------------------------- rescale
+def rescale_params(ori_shape, target_shape):
+    """Python-double ratio and padding of ``Inferer.rescale``,
+    ``yolov6/core/inferer.py:206-207``."""
+    ratio = min(ori_shape[0] / target_shape[0], ori_shape[1] / target_shape[1])
+    pad_x = (ori_shape[1] - target_shape[1] * ratio) / 2
+    pad_y = (ori_shape[0] - target_shape[0] * ratio) / 2
+    return ratio, pad_x, pad_y
+
+
+def rescale(ori_shape, boxes_and_cors, target_shape, do_round=False):
+    """``Inferer.rescale``, ``yolov6/core/inferer.py:203-228`` on ``[k,12]`` fp32.
+    ``do_round`` applies the caller's ``.round()`` (``inferer.py:100``, half-to-even)."""
+    ratio, pad_x, pad_y = rescale_params(ori_shape, target_shape)
+    v = np.array(boxes_and_cors, f32, copy=True)
+    v[:, 0::2] = (v[:, 0::2] - f32(pad_x)).astype(f32)      # :210
+    v[:, 1::2] = (v[:, 1::2] - f32(pad_y)).astype(f32)      # :211
+    v = (v / f32(ratio)).astype(f32)                        # :212  true division by the fp32-rounded scalar
+    v[:, 0::2] = np.clip(v[:, 0::2], f32(0), f32(target_shape[1]))   # :214-225
+    v[:, 1::2] = np.clip(v[:, 1::2], f32(0), f32(target_shape[0]))
+    if do_round:
+        v = np.rint(v).astype(f32)
+    return v

@@ -1,0 +1,230 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE.
+
+Run in the build container only (``/root/reference`` is not on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Imports the unmodified reference callables
+  yolov6.utils.nms.non_max_suppression          (yolov6/utils/nms.py:31)
+  yolov6.models.effidehead.Detect / build_effidehead_layer (effidehead.py:15,304)
+  yolov6.assigners.anchor_generator.generate_anchors       (anchor_generator.py:4)
+  yolov6.utils.general.dist2bbox / dist2cor                (general.py:29,51)
+  yolov6.core.inferer.Inferer.rescale                      (inferer.py:203)
+with torch CPU + torchvision 0.26.0 CPU and stores their outputs.  Large inputs
+are NOT stored: they are regenerated from ``yolo_lp_b200.synth`` and pinned by a
+SHA-256; small/edge inputs and model-derived tensors are stored in full.
+
+Oracle-driving rules: always clone (the reference mutates its
+input, nms.py:76) and call it in small chunks so its 10 s wall-clock
+``time_limit`` (nms.py:63,126-128) never fires.
+"""
+import os
+import sys
+
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, REPO)
+
+import numpy as np
+import torch
+
+from yolov6.utils.nms import non_max_suppression as ref_nms
+from yolov6.utils.general import dist2bbox as ref_dist2bbox, dist2cor as ref_dist2cor
+from yolov6.assigners.anchor_generator import generate_anchors as ref_generate_anchors
+from yolov6.models.effidehead import Detect as RefDetect, build_effidehead_layer
+from yolov6.core.inferer import Inferer as RefInferer
+
+from yolo_lp_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+torch.manual_seed(0)
+
+
+def run_ref_nms(pred, conf, iou, max_det, chunk=1):
+    outs = []
+    for s in range(0, pred.shape[0], chunk):
+        outs += ref_nms(pred[s:s + chunk].clone(), conf, iou, max_det=max_det)
+    return [o.numpy().astype(np.float32) for o in outs]
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def pack_rows(rows):
+    counts = np.array([r.shape[0] for r in rows], np.int64)
+    flat = np.concatenate(rows, 0) if len(rows) else np.zeros((0, 28), np.float32)
+    return counts, flat.astype(np.float32)
+
+
+# ----------------------------------------------------------------- seeded synthetic NMS cases
+# name -> (config id, image indices, quant, overrides)
+SEEDED = {
+    "nms_cfg1": (1, [0], None, {}),
+    "nms_cfg2": (2, [0, 1, 2, 31], None, {}),
+    "nms_cfg3": (3, [0, 100, 255], None, {}),
+    "nms_cfg4_dense": (4, [0, 63], None, {}),
+    "nms_cfg5_1280": (5, [0, 31], None, {}),
+    "nms_cfg2_ties16": (2, [0, 5], 16, {}),
+    "nms_cfg4_ties16": (4, [1], 16, {}),
+    "nms_eval_default": (2, [3, 4], None, dict(conf=0.03, iou=0.65)),
+    "nms_cfg1_maxdet5": (1, [0], None, dict(max_det=5)),
+}
+
+
+def make_seeded():
+    for name, (cid, idxs, quant, over) in SEEDED.items():
+        cfg = dict(synth.CONFIGS[cid])
+        cfg.update(over)
+        rows, shas = [], []
+        for i in idxs:
+            x = synth.synth_image(cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"], i, quant=quant)
+            shas.append(synth.sha256_of(x))
+            rows += run_ref_nms(x[None], cfg["conf"], cfg["iou"], cfg["max_det"])
+        counts, flat = pack_rows(rows)
+        save(name, config_id=cid, indices=np.array(idxs), quant=np.array(quant or 0),
+             conf=np.array(cfg["conf"]), iou=np.array(cfg["iou"]), max_det=np.array(cfg["max_det"]),
+             sha256=np.array(shas), counts=counts, rows=flat)
+        print("   counts", counts.tolist())
+
+
+# ----------------------------------------------------------------- small stored-input edge cases
+def edge_inputs():
+    g = torch.Generator().manual_seed(1234)
+    A = 96
+    cases = {}
+
+    def base(A=A, obj=None):
+        x = synth.synth_image(A, 128, 6, 24, 77, len(cases))
+        if obj is not None:
+            x[:, 4] = obj
+        return x
+
+    cases["plain"] = (base(), 0.25, 0.45, 300)
+    cases["none_pass"] = (base(), 0.99, 0.45, 300)                     # 0 survivors
+    x = base(); x[:, 13:] *= 0.01; x[17, 13:] = 0.9
+    cases["one_pass"] = (x, 0.5, 0.45, 300)                            # 1 survivor
+    cases["all_pass_maxdet7"] = (base(), 0.0, 0.45, 7)                 # k > max_det
+    cases["obj_random"] = (base(obj=torch.rand(A, generator=g)), 0.1, 0.5, 300)   # obj != 1 (nms.py:76)
+    x = base(); x[:, 2:4] = 0.0
+    cases["zero_area"] = (x, 0.0, 0.45, 300)                           # 0/0 IoU -> NaN -> never suppressed
+    x = base(); x[:, 0:4] = torch.tensor([50.0, 50.0, 20.0, 20.0])
+    cases["identical_boxes"] = (x, 0.0, 0.45, 300)                     # IoU 1 everywhere
+    # IoU exactly float32(180/400) = 0.44999998 vs thr 0.45 (double) -> kept
+    x = base(); x[:, 13:] = 0.0
+    x[0, 0:4] = torch.tensor([10.0, 10.0, 20.0, 20.0]); x[0, 13:] = 0.9
+    x[1, 0:4] = torch.tensor([4.5, 10.0, 9.0, 20.0]); x[1, 13:] = 0.8
+    cases["iou_threshold_edge"] = (x, 0.5, 0.45, 300)
+    x = base(); x[:, 13:] = torch.round(x[:, 13:] * 4) / 4
+    cases["ties_quant4"] = (x, 0.0, 0.6, 300)
+    x = base(A=33)                                                      # odd A, ragged tile
+    cases["odd_A33"] = (x, 0.05, 0.45, 300)
+    return cases
+
+
+def make_edges():
+    for name, (x, conf, iou, max_det) in edge_inputs().items():
+        rows = run_ref_nms(x[None], conf, iou, max_det)
+        counts, flat = pack_rows(rows)
+        save("nms_edge_" + name, pred=x.numpy(), conf=np.array(conf), iou=np.array(iou),
+             max_det=np.array(max_det), counts=counts, rows=flat)
+        print("   counts", counts.tolist())
+    # a batch mixing empty and non-empty images: checks per-image independence
+    xs = torch.stack([edge_inputs()["plain"][0], edge_inputs()["none_pass"][0] * 0.0, edge_inputs()["obj_random"][0]])
+    rows = run_ref_nms(xs, 0.2, 0.45, 300, chunk=3)
+    counts, flat = pack_rows(rows)
+    save("nms_edge_batch3", pred=xs.numpy(), conf=np.array(0.2), iou=np.array(0.45), max_det=np.array(300),
+         counts=counts, rows=flat)
+    print("   counts", counts.tolist())
+
+
+# ----------------------------------------------------------------- model-derived (Detect head) cases
+CLS = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5")
+
+
+def build_head(channels=(64, 128, 256), rerandomise=True):
+    ch_list = [0] * 11
+    ch_list[6], ch_list[8], ch_list[10] = channels
+    layers = build_effidehead_layer(ch_list, 1, 31, 24, 37, reg_max=0, num_layers=3)
+    head = RefDetect(31, 24, 37, 3, head_layers=layers, use_dfl=False, reg_max=0)
+    head.initialize_biases()
+    if rerandomise:   # true random-init is degenerate (all preds zeroed)
+        with torch.no_grad():
+            for name in ("pro_preds", "alp_preds", "ad0_preds", "ad1_preds", "ad2_preds", "ad3_preds",
+                         "ad4_preds", "ad5_preds", "reg_preds", "cor_preds"):
+                for conv in getattr(head, name):
+                    conv.weight.normal_(0.0, 0.5)
+    return head.eval()
+
+
+def run_head(head, B, H, W, channels=(64, 128, 256)):
+    feats = [torch.rand(B, c, H // s, W // s) for c, s in zip(channels, (8, 16, 32))]
+    raw = [dict() for _ in range(3)]
+    hooks = []
+    names = [n + "_preds" for n in CLS] + ["reg_preds", "cor_preds"]
+    for n in names:
+        for lvl, conv in enumerate(getattr(head, n)):
+            hooks.append(conv.register_forward_hook(
+                lambda m, i, o, lvl=lvl, n=n: raw[lvl].__setitem__(n[:3], o.detach().clone())))
+    with torch.no_grad():
+        out = head([f.clone() for f in feats])
+    for h in hooks:
+        h.remove()
+    return raw, out
+
+
+def make_decode():
+    for name, rer, B, H, W in (("decode_rerand_96x160", True, 1, 96, 160), ("decode_degenerate_96x160", False, 2, 96, 160),
+                               ("decode_rerand_64x64", True, 2, 64, 64)):
+        head = build_head(rerandomise=rer)
+        raw, out = run_head(head, B, H, W)
+        arrays = {}
+        for lvl in range(3):
+            for k, v in raw[lvl].items():
+                arrays[f"l{lvl}_{k}"] = v.numpy()
+        conf = 0.001 if (not rer or H == 64) else 0.02
+        rows = run_ref_nms(out, conf, 0.45, 300, chunk=B)
+        counts, flat = pack_rows(rows)
+        save(name, out=out.numpy(), conf=np.array(conf), iou=np.array(0.45), max_det=np.array(300),
+             counts=counts, rows=flat, hw=np.array([H, W]), **arrays)
+        print("   A", out.shape[1], "counts", counts.tolist())
+
+
+# ----------------------------------------------------------------- geometry + rescale KATs
+def make_geometry():
+    g = torch.Generator().manual_seed(5)
+    feats = [torch.zeros(1, 1, h, w) for h, w in ((12, 20), (6, 10), (3, 5))]
+    ap, st = ref_generate_anchors(feats, torch.tensor([8, 16, 32]), 5.0, 0.5, device="cpu", is_eval=True, mode="af")
+    dist = torch.rand((2, ap.shape[0], 4), generator=g) * 6
+    cdist = torch.rand((2, ap.shape[0], 8), generator=g) * 6 - 1
+    save("geometry", anchor_points=ap.numpy(), stride_tensor=st.numpy(), dist=dist.numpy(), cdist=cdist.numpy(),
+         bbox_xyxy=ref_dist2bbox(dist, ap, "xyxy").numpy(), bbox_xywh=ref_dist2bbox(dist, ap, "xywh").numpy(),
+         corners=ref_dist2cor(cdist, ap).numpy(), hw=np.array([(12, 20), (6, 10), (3, 5)]))
+
+
+def make_rescale():
+    g = torch.Generator().manual_seed(6)
+    arrays = {}
+    # (letterboxed H_in, W_in) , (source H0, W0)
+    shapes = [((640, 416), (1160, 720)), ((384, 640), (1080, 1920)), ((640, 640), (640, 640)),
+              ((224, 640), (375, 1242)), ((640, 640), (1160, 720)), ((1280, 1280), (2000, 3000))]
+    for n, (ori, tgt) in enumerate(shapes):
+        k = 37
+        v = torch.rand((k, 12), generator=g) * torch.tensor([ori[1], ori[0]] * 6) * 1.2 - 20.0
+        v[0, :] = 0.5                                                   # exercises round-half-even after /ratio
+        res = RefInferer.rescale(ori, v.clone(), tgt + (3,))
+        arrays[f"in{n}"] = v.numpy()
+        arrays[f"out{n}"] = res.numpy()
+        arrays[f"round{n}"] = res.round().numpy()                       # inferer.py:100
+        arrays[f"shape{n}"] = np.array([ori[0], ori[1], tgt[0], tgt[1]])
+    save("rescale", n=np.array(len(shapes)), **arrays)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale"]
+    for w in which:
+        globals()["make_" + w]()

@@ -1,0 +1,95 @@
+"""Pin the oracle (numpy restatement and torch port) to outputs of the REFERENCE
+itself (tests/golden/*.npz, made by tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lp_oracle, torch_port
+from _util import golden, golden_names, split_rows, seeded_inputs, assert_rows_equal
+
+SEEDED = [n for n in golden_names("nms_cfg") + golden_names("nms_eval")]
+EDGES = golden_names("nms_edge_")
+DECODE = golden_names("decode_")
+
+
+def _knobs(g):
+    return float(g["conf"]), float(g["iou"]), int(g["max_det"])
+
+
+@pytest.mark.parametrize("name", SEEDED)
+def test_numpy_oracle_seeded(name):
+    g = golden(name)
+    conf, iou, max_det = _knobs(g)
+    pred = seeded_inputs(g).numpy()
+    want = split_rows(g["counts"], g["rows"])
+    got = lp_oracle.non_max_suppression(pred, conf, iou, max_det=max_det)
+    for b, (a, w) in enumerate(zip(got, want)):
+        assert_rows_equal(a, w, f"{name}[{b}]")
+
+
+@pytest.mark.parametrize("name", EDGES)
+def test_numpy_oracle_edges(name):
+    g = golden(name)
+    conf, iou, max_det = _knobs(g)
+    pred = g["pred"]
+    pred = pred[None] if pred.ndim == 2 else pred
+    want = split_rows(g["counts"], g["rows"])
+    got, idx = lp_oracle.non_max_suppression(pred, conf, iou, max_det=max_det, return_index=True)
+    for b, (a, w) in enumerate(zip(got, want)):
+        assert_rows_equal(a, w, f"{name}[{b}]")
+        assert len(idx[b]) == len(a)
+
+
+@pytest.mark.parametrize("name", SEEDED[:3] + EDGES)
+def test_torch_port(name):
+    g = golden(name)
+    conf, iou, max_det = _knobs(g)
+    pred = torch.from_numpy(g["pred"]) if "pred" in g else seeded_inputs(g)
+    pred = pred[None] if pred.ndim == 2 else pred
+    want = split_rows(g["counts"], g["rows"])
+    got = torch_port.non_max_suppression(pred.clone(), conf, iou, max_det=max_det)
+    for b, (a, w) in enumerate(zip(got, want)):
+        assert_rows_equal(a.numpy(), w, f"{name}[{b}]")
+
+
+def _levels(g):
+    return [{k: g[f"l{l}_{k}"] for k in ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5", "reg", "cor")}
+            for l in range(3)]
+
+
+@pytest.mark.parametrize("name", DECODE)
+def test_decode_oracle(name):
+    g = golden(name)
+    want = g["out"]
+    got = lp_oracle.detect_decode(_levels(g), (8, 16, 32))
+    assert got.shape == want.shape
+    # geometry columns and obj are exactly restatable; sigmoid is held to 1e-5 rel
+    assert np.array_equal(got[..., :13].view(np.uint32), want[..., :13].view(np.uint32))
+    np.testing.assert_allclose(got[..., 13:], want[..., 13:], rtol=1e-5, atol=0)
+    tp = torch_port.detect_decode([{k: torch.from_numpy(v) for k, v in lv.items()} for lv in _levels(g)], (8, 16, 32))
+    np.testing.assert_allclose(tp.numpy(), want, rtol=1e-6, atol=0)
+    # NMS on the reference's own decoded tensor
+    rows = lp_oracle.non_max_suppression(want, *_knobs(g)[:2], max_det=_knobs(g)[2])
+    for b, (a, w) in enumerate(zip(rows, split_rows(g["counts"], g["rows"]))):
+        assert_rows_equal(a, w, f"{name}[{b}]")
+
+
+def test_geometry_oracle():
+    g = golden("geometry")
+    ap, st = lp_oracle.generate_anchors_eval([tuple(x) for x in g["hw"].tolist()], (8, 16, 32))
+    assert np.array_equal(ap, g["anchor_points"]) and np.array_equal(st, g["stride_tensor"])
+    assert np.array_equal(lp_oracle.dist2bbox(g["dist"], ap, "xyxy"), g["bbox_xyxy"])
+    assert np.array_equal(lp_oracle.dist2bbox(g["dist"], ap, "xywh"), g["bbox_xywh"])
+    assert np.array_equal(lp_oracle.dist2cor(g["cdist"], ap), g["corners"])
+
+
+def test_rescale_oracle():
+    g = golden("rescale")
+    for n in range(int(g["n"])):
+        hi, wi, h0, w0 = g[f"shape{n}"].tolist()
+        got = lp_oracle.rescale((hi, wi), g[f"in{n}"], (h0, w0, 3))
+        assert np.array_equal(got.view(np.uint32), g[f"out{n}"].view(np.uint32)), n
+        got = lp_oracle.rescale((hi, wi), g[f"in{n}"], (h0, w0, 3), do_round=True)
+        assert np.array_equal(got, g[f"round{n}"]), n
+        tp = torch_port.rescale((hi, wi), torch.from_numpy(g[f"in{n}"].copy()), (h0, w0, 3))
+        assert np.array_equal(tp.numpy().view(np.uint32), g[f"out{n}"].view(np.uint32)), n

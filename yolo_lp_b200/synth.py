@@ -1,0 +1,84 @@
+"""Deterministic synthetic head tensors ``[B, A, 290]`` for the five BASELINE.json
+workloads.
+
+Content of image ``i`` depends only on ``(seed, global index i)`` (RNG seed
+``seed * 10**6 + i``), never on how the batch is sharded across GPUs.
+
+The generator uses only ``torch.rand``/``randint``/``randperm`` on a CPU
+``torch.Generator`` plus correctly-rounded ``+ - *`` -- no ``randn``, ``exp`` or
+``sigmoid`` -- so the bits are identical on every host ISA; the golden fixtures
+pin a SHA-256 of the regenerated input.  The distribution follows SURVEY.md
+§8-d in shape: background class scores ~0.01-0.1, ``n_pos`` anchors per image
+carrying one confident class per group, boxes clustered round ``n_plates``
+plate centres.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import torch
+
+ROW = 290
+GROUPS = ((13, 44), (44, 68), (68, 105), (105, 142), (142, 179), (179, 216), (216, 253), (253, 290))
+
+#: BASELINE.json configs -> concrete inputs and NMS knobs.
+CONFIGS = {
+    1: dict(B=1, A=8400, img=640, n_plates=24, n_pos=200, conf=0.25, iou=0.45, max_det=1000, seed=0),
+    2: dict(B=32, A=8400, img=640, n_plates=24, n_pos=300, conf=0.25, iou=0.45, max_det=300, seed=1),
+    3: dict(B=256, A=8400, img=640, n_plates=24, n_pos=300, conf=0.25, iou=0.45, max_det=300, seed=2),
+    4: dict(B=64, A=8400, img=640, n_plates=24, n_pos=300, conf=0.001, iou=0.65, max_det=300, seed=3),
+    5: dict(B=32, A=33600, img=1280, n_plates=96, n_pos=4096, conf=0.25, iou=0.45, max_det=300, seed=4),
+}
+
+
+def level_shapes(img_h: int, img_w: int, strides=(8, 16, 32)):
+    """Feature-map sizes of the three head levels for a letterboxed input."""
+    return [(img_h // s, img_w // s) for s in strides]
+
+
+def synth_image(A: int, img: int, n_plates: int, n_pos: int, seed: int, index: int,
+                quant: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """One image's ``[A, 290]`` fp32 head rows (CPU)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed * 10**6 + index)
+    x = out if out is not None else torch.empty((A, ROW), dtype=torch.float32)
+    centres = torch.rand((n_plates, 2), generator=g) * float(img)
+    assign = torch.randint(n_plates, (A,), generator=g)
+    r = torch.rand((4, A, 2), generator=g)                             # explicit adds: no ISA-dependent
+    jitter = (((r[0] + r[1]) + r[2]) + r[3]) - 2.0                     # reduction order; ~N(0, 1/3)
+    cxy = centres[assign] + jitter * 10.392304845413264               # std 6 px
+    wh = torch.rand((A, 2), generator=g) * 60.0 + 20.0
+    x[:, 0:2] = cxy
+    x[:, 2:4] = wh
+    x[:, 4] = 1.0                                                      # effidehead.py:290
+    x[:, 5:13] = cxy.repeat(1, 4) + (torch.rand((A, 8), generator=g) - 0.5) * wh.repeat(1, 4)
+    u = torch.rand((A, ROW - 13), generator=g)
+    u2 = u * u
+    cls = (u2 * u2 * u2) * 0.1 + 0.002                                 # background ~0.002..0.1
+    n_pos = min(n_pos, A)
+    pos = torch.randperm(A, generator=g)[:n_pos]
+    for s, e in GROUPS:
+        j = torch.randint(e - s, (n_pos,), generator=g)
+        cls[pos, (s - 13) + j] = torch.rand((n_pos,), generator=g) * 0.5 + 0.45
+    if quant:
+        cls = torch.round(cls * float(quant)) / float(quant)           # mass ties
+    x[:, 13:] = cls
+    return x
+
+
+def synth_head(B: int, A: int, img: int, n_plates: int, n_pos: int, seed: int,
+               first_index: int = 0, quant: int | None = None, pin_memory: bool = False, **_) -> torch.Tensor:
+    """``[B, A, 290]`` fp32 on CPU; images ``first_index .. first_index+B-1`` of the stream."""
+    out = torch.empty((B, A, ROW), dtype=torch.float32, pin_memory=pin_memory)
+    for b in range(B):
+        synth_image(A, img, n_plates, n_pos, seed, first_index + b, quant=quant, out=out[b])
+    return out
+
+
+def sha256_of(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
+
+
+def shard_range(B: int, rank: int, world: int):
+    """Contiguous image range of ``rank``: ``[g*B/G, (g+1)*B/G)``."""
+    return (rank * B) // world, ((rank + 1) * B) // world
