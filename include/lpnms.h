@@ -1,0 +1,147 @@
+/*
+ * lpnms.h -- C ABI of the B200-native YOLO-LP post-processing library
+ *            (liblpnms.so, hand-written sm_100a CUDA, no torch types).
+ *
+ * The reference (KyleHuang9/YOLO-LP) exposes this path as plain Python
+ * callables, not as an FFI; the entry points below are what a ctypes binding
+ * for each of those callables binds (see INTEGRATION.md for the stubs):
+ *
+ *   lp_nms_f32               <- yolov6/utils/nms.py:31-130  non_max_suppression
+ *                               (+ torchvision.ops.nms, call site nms.py:121,
+ *                                + xywh2xyxy nms.py:21-28)
+ *   lp_detect_decode_f32     <- yolov6/models/effidehead.py:247-301
+ *                               Detect.forward eval tail (after the convs)
+ *   lp_generate_anchors_f32  <- yolov6/assigners/anchor_generator.py:11-31
+ *   lp_dist2bbox_f32         <- yolov6/utils/general.py:29-40
+ *   lp_dist2cor_f32          <- yolov6/utils/general.py:51-66
+ *   lp_xywh2xyxy_f32         <- yolov6/utils/nms.py:21-28
+ *   lp_rescale_f32           <- yolov6/core/inferer.py:203-228 (+ .round() :100)
+ *   lp_rescale_batch_f32     <- same, one launch for a whole [B,max_det,28] batch
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     parameter name ends in _host;
+ *   - the library never allocates, frees or synchronises; all work is queued on
+ *     the cudaStream_t passed as `stream` (void* here so C callers need no CUDA
+ *     headers); it keeps no global state and is re-entrant;
+ *   - every function returns int: 0 = ok, <0 = LP_E_* argument error,
+ *     >0 = cudaError_t of a failed launch; nothing throws, aborts or exits.
+ */
+#ifndef LPNMS_H_
+#define LPNMS_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LP_VERSION 100            /* major*10000 + minor*100 + patch */
+#define LP_ROW 290                /* floats per head row: 4 box | 1 obj | 8 corners | 31 | 24 | 6x37 */
+#define LP_OUT 28                 /* floats per detection: 4 xyxy | 8 corners | 8 conf | 8 argmax */
+#define LP_MAX_LEVELS 4
+#define LP_MAX_NMS_DEFAULT 30000  /* yolov6/utils/nms.py:62 */
+
+#define LP_OK 0
+#define LP_E_NULL (-1)            /* required pointer is NULL */
+#define LP_E_SIZE (-2)            /* negative / zero / overflowing size */
+#define LP_E_ALIGN (-3)           /* pointer not aligned as documented */
+#define LP_E_WORKSPACE (-4)       /* workspace smaller than lp_nms_workspace_bytes() */
+#define LP_E_THRESHOLD (-5)       /* conf/iou threshold outside [0,1] (nms.py:57-58) */
+#define LP_E_ARG (-6)             /* any other bad argument */
+
+#if defined(__GNUC__)
+#define LP_API __attribute__((visibility("default")))
+#else
+#define LP_API
+#endif
+
+typedef void* lp_stream_t;        /* cudaStream_t */
+
+/* One FPN level of raw prediction-conv outputs, NCHW fp32 contiguous:
+ * cls[0..7] = pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w]; reg[B,4,h,w]; cor[B,8,h,w]. */
+typedef struct lp_level {
+    const float* cls[8];
+    const float* reg;
+    const float* cor;
+    int h;
+    int w;
+    float stride;
+} lp_level_t;
+
+LP_API int lp_version(void);
+LP_API const char* lp_error_string(int code);
+
+/* Bytes of device scratch lp_nms_f32 needs for (B images, A anchors, max_det). */
+LP_API int lp_nms_workspace_bytes(int B, int A, int max_det, size_t* out_bytes);
+
+/*
+ * Confidence filter + greedy NMS over pred[B,A,290] (contiguous, 16-byte
+ * aligned, NOT modified -- the reference's in-place `x[:,13:] *= x[:,4:5]`
+ * side effect, nms.py:76, is not reproduced).
+ *   conf_thres  compared in fp32 as (float)conf_thres       (nms.py:90-91)
+ *   iou_thres   compared as (double)iou_f32 > iou_thres     (torchvision CPU kernel)
+ *   max_det     rows kept per image                         (nms.py:122-123)
+ *   max_nms     candidates entering NMS, 30000 in nms.py:62; ties at the cut are
+ *               broken (score desc, anchor asc) where the reference is unstable
+ * Outputs: out[B,max_det,28] (rows >= counts[b] untouched), counts[B],
+ * kept_anchor[B,max_det] (anchor index of every kept row; may be NULL).
+ * rescale (may be NULL): [B,5] fp32 = pad_x, pad_y, ratio, W0, H0 per image;
+ * when given, columns 0..11 of every kept row are mapped back to source
+ * coordinates exactly as lp_rescale_f32 does (round applied iff do_round).
+ */
+LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres,
+               int max_det, int max_nms, void* workspace, size_t workspace_bytes,
+               float* out, int* counts, int* kept_anchor,
+               const float* rescale, int do_round, lp_stream_t stream);
+
+/*
+ * The two stages of lp_nms_f32, separately launchable (profiling, per-stage timing):
+ *   lp_nms_filter_f32    K1: nms.py:76-97 + :120 -- scores every row of pred once, leaves the
+ *                        surviving candidates' sort keys and per-image counts in `workspace`;
+ *   lp_nms_suppress_f32  K2: sort + torchvision.ops.nms (nms.py:121) + keep[:max_det] (:122-123)
+ *                        + output rows, reading what K1 left in the same `workspace`.
+ * lp_nms_f32 == lp_nms_filter_f32 followed by lp_nms_suppress_f32 on the same stream.
+ */
+LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
+                             size_t workspace_bytes, lp_stream_t stream);
+LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
+                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                               const float* rescale, int do_round, lp_stream_t stream);
+
+/* Detect.forward eval tail: raw per-level conv outputs -> out[B,A,290],
+ * A = sum h*w, levels in order; anchors are computed from the index, never
+ * materialised. */
+LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int B, float* out, lp_stream_t stream);
+
+/* generate_anchors(is_eval=True, mode='af'): anchor_points[A,2], stride_tensor[A]. */
+LP_API int lp_generate_anchors_f32(const int* h_host, const int* w_host, const float* stride_host, int n_levels,
+                            float grid_cell_offset, float* anchor_points, float* stride_tensor, lp_stream_t stream);
+
+/* dist2bbox: distance[n,A,4] (ltrb) + anchor_points[A,2] -> out[n,A,4]; xywh != 0 selects 'xywh'. */
+LP_API int lp_dist2bbox_f32(const float* distance, const float* anchor_points, long long n, int A, int xywh,
+                     float* out, lp_stream_t stream);
+
+/* dist2cor: distance[n,A,8] + anchor_points[A,2] -> out[n,A,8] (TL, BL, BR, TR). */
+LP_API int lp_dist2cor_f32(const float* distance, const float* anchor_points, long long n, int A,
+                    float* out, lp_stream_t stream);
+
+/* xywh2xyxy on n rows; in/out row strides in floats (>= 4). in == out allowed. */
+LP_API int lp_xywh2xyxy_f32(const float* in, long long n, long long in_stride, float* out, long long out_stride,
+                     lp_stream_t stream);
+
+/* Inferer.rescale on k rows of 12 coords (row stride in floats), in place:
+ * v = (v - pad) / ratio (true fp32 division), clamp x to [0,W0], y to [0,H0],
+ * then round-half-even iff do_round.  pad/ratio are the reference's Python
+ * doubles rounded to fp32 by the caller. */
+LP_API int lp_rescale_f32(float* rows, long long k, long long row_stride, float pad_x, float pad_y, float ratio,
+                   float w0, float h0, int do_round, lp_stream_t stream);
+
+/* Same over det[B,max_det,28] with counts[B] and params[B,5] = pad_x,pad_y,ratio,W0,H0. */
+LP_API int lp_rescale_batch_f32(float* det, const int* counts, int B, int max_det, const float* params,
+                         int do_round, lp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LPNMS_H_ */

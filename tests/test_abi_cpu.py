@@ -1,0 +1,88 @@
+"""CPU-only checks of the C-ABI boundary: the library loads without a GPU, exports every
+symbol include/lpnms.h declares, and validates its arguments before touching CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from yolo_lp_b200 import _abi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()           # no-op when liblpnms.so is newer than its sources
+    return _abi.load()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lpnms.h")).read()
+    return sorted(set(re.findall(r"LP_API\s+[\w\s\*]+?\b(lp_\w+)\s*\(", text)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 11
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lpnms.h but not exported"
+        assert n in _abi.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_abi.SIGNATURES) == names
+
+
+def test_version_and_errors(lib):
+    assert lib.lp_version() == 100
+    assert lib.lp_error_string(0) == b"ok"
+    assert b"threshold" in lib.lp_error_string(-5)
+    assert b"workspace" in lib.lp_error_string(-4)
+
+
+def test_workspace_query(lib):
+    small = _abi.nms_workspace_bytes(1, 8400, 300)
+    big = _abi.nms_workspace_bytes(32, 8400, 300)
+    assert 0 < small < big
+    assert big >= 32 * 8400 * 8                      # one 64-bit key per anchor
+    assert _abi.nms_workspace_bytes(32, 33600, 300) >= 32 * 65536 * 8   # pow2-padded for the global sort
+    n = ctypes.c_size_t()
+    assert lib.lp_nms_workspace_bytes(0, 8400, 300, ctypes.byref(n)) == -2
+    assert lib.lp_nms_workspace_bytes(1, 8400, 300, None) == -1
+    assert lib.lp_nms_workspace_bytes(1 << 20, 1 << 20, 300, ctypes.byref(n)) == -2
+
+
+def test_argument_validation_without_gpu(lib):
+    # every check below is rejected before any CUDA call is made
+    f = lib.lp_nms_f32
+    assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None) == -1
+    buf = ctypes.create_string_buffer(1 << 16)
+    base = ctypes.addressof(buf)
+    p = (base + 255) // 256 * 256
+    args = dict(pred=p, ws=p + 4096, out=p + 32768, counts=p + 49152)
+    assert f(args["pred"], 1, 8, 1.5, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -5
+    assert f(args["pred"], 1, 8, 0.25, -0.1, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -5
+    assert f(args["pred"] + 8, 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -3
+    assert f(args["pred"], 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 16, args["out"], args["counts"], None, None, 0, None) == -4
+    assert f(args["pred"], 0, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -2
+    assert lib.lp_rescale_f32(p, 4, 8, 0.0, 0.0, 1.0, 10.0, 10.0, 0, None) == -2     # row stride < 12
+    assert lib.lp_rescale_f32(p, 4, 12, 0.0, 0.0, 0.0, 10.0, 10.0, 0, None) == -6    # ratio must be > 0
+    assert lib.lp_dist2bbox_f32(p + 4, p, 1, 8, 0, p, None) == -3
+    assert lib.lp_detect_decode_f32(None, 3, 1, p, None) == -1
+
+
+def test_check_maps_errors_like_the_reference(lib):
+    with pytest.raises(AssertionError):
+        _abi.check("lp_nms_f32", -5)          # nms.py:57-58 raise AssertionError
+    with pytest.raises(ValueError):
+        _abi.check("lp_nms_f32", -2)
+    with pytest.raises(_abi.LpError):
+        _abi.check("lp_nms_f32", 700)
+    _abi.check("lp_nms_f32", 0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "yolo_lp_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+            assert "/root/reference" not in src, fn

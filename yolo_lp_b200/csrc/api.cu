@@ -1,0 +1,272 @@
+// extern "C" boundary of liblpnms.so (see include/lpnms.h): argument validation, workspace
+// carving and kernel launches.  No allocation, no synchronisation, no global mutable state
+// (the SM count is cached per device; that cache is idempotent).
+#include <math.h>
+
+#include "kernels.cuh"
+
+namespace lp {
+
+constexpr size_t WS_ALIGN = 256;
+
+static inline size_t align_up(size_t x) { return (x + WS_ALIGN - 1) / WS_ALIGN * WS_ALIGN; }
+static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+static unsigned pow2_at_least(unsigned n) {
+    unsigned p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// Per-image key stride: A when the candidates always fit the shared-memory sort, else the next
+// power of two (the global-memory bitonic path pads in place).
+static unsigned key_stride_for(unsigned A) {
+    return pow2_at_least(A) <= (unsigned)nms_sort_smem_keys(A) ? A : pow2_at_least(A);
+}
+
+struct WsLayout {
+    size_t counts, keys, kept_box, kept_anchor, total;
+};
+static WsLayout ws_layout(int B, int A, int max_det) {
+    WsLayout w;
+    size_t off = 0;
+    w.counts = off;      off = align_up(off + sizeof(int) * (size_t)B);
+    w.keys = off;        off = align_up(off + sizeof(unsigned long long) * (size_t)B * key_stride_for(A));
+    w.kept_box = off;    off = align_up(off + sizeof(float4) * (size_t)B * (size_t)max_det);
+    w.kept_anchor = off; off = align_up(off + sizeof(int) * (size_t)B * (size_t)max_det);
+    w.total = off;
+    return w;
+}
+
+static int num_sms_cached() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+static bool size_ok(int B, int A, int max_det) {
+    if (B <= 0 || A <= 0 || max_det < 0) return false;
+    if ((long long)B * A >= (1ll << 31) - 64) return false;         // row index fits 32 bits
+    if ((long long)B * (long long)max_det >= (1ll << 31)) return false;
+    return true;
+}
+
+}  // namespace lp
+
+using namespace lp;
+
+extern "C" {
+
+LP_API int lp_version(void) { return LP_VERSION; }
+
+LP_API const char* lp_error_string(int code) {
+    switch (code) {
+        case LP_OK: return "ok";
+        case LP_E_NULL: return "required pointer is NULL";
+        case LP_E_SIZE: return "bad size";
+        case LP_E_ALIGN: return "pointer is not aligned as required";
+        case LP_E_WORKSPACE: return "workspace too small";
+        case LP_E_THRESHOLD: return "threshold outside [0, 1]";
+        case LP_E_ARG: return "bad argument";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+LP_API int lp_nms_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) {
+    if (!out_bytes) return LP_E_NULL;
+    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
+    *out_bytes = ws_layout(B, A, max_det).total;
+    return LP_OK;
+}
+
+// shared validation + parameter setup of the two NMS stages
+static int nms_setup(const float* pred, int B, int A, int max_det, void* workspace, size_t workspace_bytes,
+                     FilterParams& f, NmsParams& n) {
+    if (!pred || !workspace) return LP_E_NULL;
+    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
+    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN)) return LP_E_ALIGN;
+    const WsLayout w = ws_layout(B, A, max_det);
+    if (workspace_bytes < w.total) return LP_E_WORKSPACE;
+    char* ws = static_cast<char*>(workspace);
+    f.pred = pred;
+    f.total_rows = (unsigned)B * (unsigned)A;
+    f.A = (unsigned)A;
+    f.n_tiles = (f.total_rows + 31u) / 32u;
+    f.conf = 0.0f;
+    f.keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
+    f.counts = reinterpret_cast<int*>(ws + w.counts);
+    f.key_stride = key_stride_for((unsigned)A);
+    n.pred = pred;
+    n.A = (unsigned)A;
+    n.keys = f.keys;
+    n.key_stride = f.key_stride;
+    n.counts = f.counts;
+    n.iou_floor = 0.0f;
+    n.max_det = max_det;
+    n.max_nms = LP_MAX_NMS_DEFAULT;
+    n.kept_box = reinterpret_cast<float4*>(ws + w.kept_box);
+    n.kept_anchor_ws = reinterpret_cast<int*>(ws + w.kept_anchor);
+    n.out = nullptr;
+    n.out_counts = nullptr;
+    n.kept_anchor = nullptr;
+    n.rescale = nullptr;
+    n.do_round = 0;
+    n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
+    return LP_OK;
+}
+
+LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
+                             size_t workspace_bytes, lp_stream_t stream) {
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
+    FilterParams f;
+    NmsParams n;
+    const int rc = nms_setup(pred, B, A, 0, workspace, (size_t)-1, f, n);
+    if (rc != LP_OK) return rc;
+    // the layout up to the keys does not depend on max_det; require at least counts + keys
+    const WsLayout w = ws_layout(B, A, 0);
+    if (workspace_bytes < w.kept_box) return LP_E_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * (size_t)B, s);
+    if (e != cudaSuccess) return (int)e;
+    f.conf = (float)conf_thres;  // tensor >= python-scalar compares in fp32
+    return (int)launch_filter(f, num_sms_cached(), s);
+}
+
+LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
+                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                               const float* rescale, int do_round, lp_stream_t stream) {
+    if (!counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (max_nms <= 0) return LP_E_SIZE;
+    if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    if (!aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    FilterParams f;
+    NmsParams n;
+    const int rc = nms_setup(pred, B, A, max_det, workspace, workspace_bytes, f, n);
+    if (rc != LP_OK) return rc;
+    // (double)ovr > iou_thres  <=>  ovr > largest float <= iou_thres
+    float iou_floor = (float)iou_thres;
+    if ((double)iou_floor > iou_thres) iou_floor = nextafterf(iou_floor, -INFINITY);
+    n.iou_floor = iou_floor;
+    n.max_nms = max_nms;
+    n.out = out;
+    n.out_counts = counts;
+    n.kept_anchor = kept_anchor;
+    n.rescale = rescale;
+    n.do_round = do_round;
+    return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+               const float* rescale, int do_round, lp_stream_t stream) {
+    // validate everything before queueing anything
+    if (!pred || !workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (!size_ok(B, A, max_det) || max_nms <= 0) return LP_E_SIZE;
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
+    int rc = lp_nms_filter_f32(pred, B, A, conf_thres, workspace, workspace_bytes, stream);
+    if (rc != LP_OK) return rc;
+    return lp_nms_suppress_f32(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                               kept_anchor, rescale, do_round, stream);
+}
+
+LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream) {
+    if (!levels || !out) return LP_E_NULL;
+    if (n_levels <= 0 || n_levels > LP_MAX_LEVELS || B <= 0 || B > 65535) return LP_E_SIZE;
+    if (!aligned(out, 8)) return LP_E_ALIGN;
+    DecodeParams p;
+    long long A = 0;
+    int tiles = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const lp_level_t& src = levels[l];
+        if (src.h <= 0 || src.w <= 0) return LP_E_SIZE;
+        if (!src.reg || !src.cor) return LP_E_NULL;
+        DecodeLevel& d = p.lv[l];
+        for (int g = 0; g < 8; ++g) {
+            if (!src.cls[g]) return LP_E_NULL;
+            d.cls[g] = src.cls[g];
+        }
+        d.reg = src.reg;
+        d.cor = src.cor;
+        d.w = src.w;
+        d.hw = src.h * src.w;
+        d.anchor_off = (int)A;
+        d.tile_off = tiles;
+        d.stride = src.stride;
+        A += d.hw;
+        tiles += (d.hw + DEC_TILE - 1) / DEC_TILE;
+        if (A * (long long)B >= (1ll << 31)) return LP_E_SIZE;
+    }
+    for (int l = n_levels; l < LP_MAX_LEVELS; ++l) p.lv[l] = p.lv[0];
+    p.n_levels = n_levels;
+    p.A = (int)A;
+    p.out = out;
+    return (int)launch_decode(p, tiles, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_generate_anchors_f32(const int* h, const int* w, const float* stride, int n_levels, float grid_cell_offset,
+                            float* anchor_points, float* stride_tensor, lp_stream_t stream) {
+    if (!h || !w || !stride || !anchor_points || !stride_tensor) return LP_E_NULL;
+    if (n_levels <= 0 || n_levels > LP_MAX_LEVELS) return LP_E_SIZE;
+    AnchorLevels lv;
+    long long A = 0;
+    for (int l = 0; l < LP_MAX_LEVELS; ++l) {
+        const int s = l < n_levels ? l : 0;
+        if (h[s] <= 0 || w[s] <= 0) return LP_E_SIZE;
+        lv.w[l] = w[s];
+        lv.hw[l] = h[s] * w[s];
+        lv.off[l] = (int)A;
+        lv.stride[l] = stride[s];
+        if (l < n_levels) A += lv.hw[l];
+        if (A >= (1ll << 31)) return LP_E_SIZE;
+    }
+    lv.n_levels = n_levels;
+    lv.A = (int)A;
+    lv.offset = grid_cell_offset;
+    return (int)launch_anchors(lv, anchor_points, stride_tensor, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_dist2bbox_f32(const float* distance, const float* anchor_points, long long n, int A, int xywh, float* out,
+                     lp_stream_t stream) {
+    if (!distance || !anchor_points || !out) return LP_E_NULL;
+    if (n < 0 || A <= 0) return LP_E_SIZE;
+    if (!aligned(distance, 16) || !aligned(out, 16) || !aligned(anchor_points, 8)) return LP_E_ALIGN;
+    return (int)launch_dist2bbox(distance, anchor_points, n, A, xywh, out, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_dist2cor_f32(const float* distance, const float* anchor_points, long long n, int A, float* out, lp_stream_t stream) {
+    if (!distance || !anchor_points || !out) return LP_E_NULL;
+    if (n < 0 || A <= 0) return LP_E_SIZE;
+    if (!aligned(distance, 16) || !aligned(out, 16) || !aligned(anchor_points, 8)) return LP_E_ALIGN;
+    return (int)launch_dist2cor(distance, anchor_points, n, A, out, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_xywh2xyxy_f32(const float* in, long long n, long long in_stride, float* out, long long out_stride, lp_stream_t stream) {
+    if (!in || !out) return LP_E_NULL;
+    if (n < 0 || in_stride < 4 || out_stride < 4) return LP_E_SIZE;
+    return (int)launch_xywh2xyxy(in, n, in_stride, out, out_stride, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_rescale_f32(float* rows, long long k, long long row_stride, float pad_x, float pad_y, float ratio, float w0,
+                   float h0, int do_round, lp_stream_t stream) {
+    if (!rows && k > 0) return LP_E_NULL;
+    if (k < 0 || row_stride < 12) return LP_E_SIZE;
+    if (!(ratio > 0.0f)) return LP_E_ARG;
+    return (int)launch_rescale(rows, k, row_stride, pad_x, pad_y, ratio, w0, h0, do_round, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_rescale_batch_f32(float* det, const int* counts, int B, int max_det, const float* params, int do_round,
+                         lp_stream_t stream) {
+    if (!det || !counts || !params) return LP_E_NULL;
+    if (B <= 0 || B > 65535 || max_det < 0) return LP_E_SIZE;
+    return (int)launch_rescale_batch(det, counts, B, max_det, params, do_round, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

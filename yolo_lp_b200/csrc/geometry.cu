@@ -1,0 +1,118 @@
+// Stand-alone geometry entry points that keep the reference's helper signatures alive
+// (they are also called by the training losses, which stay untouched):
+//   generate_anchors(is_eval=True, mode='af')   yolov6/assigners/anchor_generator.py:11-31
+//   dist2bbox                                   yolov6/utils/general.py:29-40
+//   dist2cor                                    yolov6/utils/general.py:51-66
+//   xywh2xyxy                                   yolov6/utils/nms.py:21-28
+//   Inferer.rescale (+ caller's .round())       yolov6/core/inferer.py:203-228, :100
+// All are tiny element-wise kernels (launch-latency bound); the hot path never calls them --
+// K-decode and K2 fuse the same arithmetic.
+#include "kernels.cuh"
+
+namespace lp {
+
+__global__ void anchors_kernel(const AnchorLevels lv, float* __restrict__ points, float* __restrict__ strides) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= lv.A) return;
+    int l = 0;
+#pragma unroll
+    for (int i = 1; i < LP_MAX_LEVELS; ++i)
+        if (i < lv.n_levels && a >= lv.off[i]) l = i;
+    const int pos = a - lv.off[l];
+    const int y = pos / lv.w[l], x = pos - y * lv.w[l];
+    points[2 * a] = __fadd_rn((float)x, lv.offset);
+    points[2 * a + 1] = __fadd_rn((float)y, lv.offset);
+    strides[a] = lv.stride[l];
+}
+
+__global__ void dist2bbox_kernel(const float4* __restrict__ dist, const float2* __restrict__ ap, long long total, int A,
+                                 int xywh, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 a = ap[i % A];
+    const float4 d = dist[i];
+    const float x1 = __fsub_rn(a.x, d.x), y1 = __fsub_rn(a.y, d.y), x2 = __fadd_rn(a.x, d.z), y2 = __fadd_rn(a.y, d.w);
+    out[i] = xywh ? make_float4(__fmul_rn(__fadd_rn(x1, x2), 0.5f), __fmul_rn(__fadd_rn(y1, y2), 0.5f),
+                                __fsub_rn(x2, x1), __fsub_rn(y2, y1))
+                  : make_float4(x1, y1, x2, y2);
+}
+
+__global__ void dist2cor_kernel(const float4* __restrict__ dist, const float2* __restrict__ ap, long long total, int A,
+                                float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float2 a = ap[i % A];
+    const float4 d0 = dist[2 * i], d1 = dist[2 * i + 1];
+    out[2 * i] = make_float4(__fsub_rn(a.x, d0.x), __fsub_rn(a.y, d0.y), __fsub_rn(a.x, d0.z), __fadd_rn(a.y, d0.w));
+    out[2 * i + 1] = make_float4(__fadd_rn(a.x, d1.x), __fadd_rn(a.y, d1.y), __fadd_rn(a.x, d1.z), __fsub_rn(a.y, d1.w));
+}
+
+__global__ void xywh2xyxy_kernel(const float* __restrict__ in, long long n, long long in_stride, float* out, long long out_stride) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = in + i * in_stride;
+    const float4 b = xywh_to_xyxy(r[0], r[1], r[2], r[3]);
+    float* o = out + i * out_stride;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w;
+}
+
+__global__ void rescale_kernel(float* rows, long long k, long long row_stride, float pad_x, float pad_y, float ratio,
+                               float w0, float h0, int do_round) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k * 12) return;
+    const long long r = i / 12;
+    const int c = (int)(i - r * 12);
+    float* v = rows + r * row_stride + c;
+    *v = (c & 1) ? rescale_coord(*v, pad_y, ratio, h0, do_round) : rescale_coord(*v, pad_x, ratio, w0, do_round);
+}
+
+__global__ void rescale_batch_kernel(float* det, const int* __restrict__ counts, int max_det,
+                                     const float* __restrict__ params, int do_round) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(counts[b], max_det);
+    if (i >= n * 12) return;
+    const int r = i / 12, c = i - r * 12;
+    const float* q = params + (size_t)b * 5;
+    float* v = det + ((size_t)b * max_det + r) * OUTW + c;
+    *v = (c & 1) ? rescale_coord(*v, q[1], q[2], q[4], do_round) : rescale_coord(*v, q[0], q[2], q[3], do_round);
+}
+
+static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t launch_anchors(const AnchorLevels& lv, float* points, float* strides, cudaStream_t s) {
+    if (lv.A <= 0) return cudaSuccess;
+    anchors_kernel<<<blocks_for(lv.A, 256), 256, 0, s>>>(lv, points, strides);
+    return cudaGetLastError();
+}
+cudaError_t launch_dist2bbox(const float* d, const float* ap, long long n, int A, int xywh, float* out, cudaStream_t s) {
+    const long long total = n * A;
+    if (total <= 0) return cudaSuccess;
+    dist2bbox_kernel<<<blocks_for(total, 256), 256, 0, s>>>((const float4*)d, (const float2*)ap, total, A, xywh, (float4*)out);
+    return cudaGetLastError();
+}
+cudaError_t launch_dist2cor(const float* d, const float* ap, long long n, int A, float* out, cudaStream_t s) {
+    const long long total = n * A;
+    if (total <= 0) return cudaSuccess;
+    dist2cor_kernel<<<blocks_for(total, 256), 256, 0, s>>>((const float4*)d, (const float2*)ap, total, A, (float4*)out);
+    return cudaGetLastError();
+}
+cudaError_t launch_xywh2xyxy(const float* in, long long n, long long is, float* out, long long os, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    xywh2xyxy_kernel<<<blocks_for(n, 256), 256, 0, s>>>(in, n, is, out, os);
+    return cudaGetLastError();
+}
+cudaError_t launch_rescale(float* rows, long long k, long long rs, float px, float py, float ratio, float w0, float h0,
+                           int do_round, cudaStream_t s) {
+    if (k <= 0) return cudaSuccess;
+    rescale_kernel<<<blocks_for(k * 12, 256), 256, 0, s>>>(rows, k, rs, px, py, ratio, w0, h0, do_round);
+    return cudaGetLastError();
+}
+cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_det, const float* params, int do_round,
+                                 cudaStream_t s) {
+    if (B <= 0 || max_det <= 0) return cudaSuccess;
+    rescale_batch_kernel<<<dim3(blocks_for((long long)max_det * 12, 256), B), 256, 0, s>>>(det, counts, max_det, params, do_round);
+    return cudaGetLastError();
+}
+
+}  // namespace lp

@@ -1,0 +1,77 @@
+// Kernel parameter blocks and host-side launchers shared by the translation units of liblpnms.
+#pragma once
+#include "common.cuh"
+
+namespace lp {
+
+// ---- K1 filter.cu ------------------------------------------------------------------------------
+struct FilterParams {
+    const float* pred;            // [total_rows, 290]
+    unsigned total_rows;          // B*A
+    unsigned A;
+    unsigned n_tiles;
+    float conf;                   // (float)conf_thres
+    unsigned long long* keys;     // [B, key_stride]
+    int* counts;                  // [B], zeroed before launch
+    unsigned key_stride;
+};
+cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t stream);
+
+// ---- K2 nms.cu ---------------------------------------------------------------------------------
+struct NmsParams {
+    const float* pred;          // [B, A, 290]
+    unsigned A;
+    unsigned long long* keys;   // [B, key_stride]
+    unsigned key_stride;
+    const int* counts;          // [B] candidates per image (from K1)
+    float iou_floor;            // largest float <= iou_thres
+    int max_det;
+    int max_nms;
+    float4* kept_box;           // [B, max_det] workspace
+    int* kept_anchor_ws;        // [B, max_det] workspace
+    float* out;                 // [B, max_det, 28]
+    int* out_counts;            // [B]
+    int* kept_anchor;           // [B, max_det] or null
+    const float* rescale;       // [B, 5] or null
+    int do_round;
+    int sort_smem_keys;         // capacity of the shared-memory sort buffer (power of two)
+};
+cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
+int nms_sort_smem_keys(unsigned A);
+
+// ---- decode.cu ---------------------------------------------------------------------------------
+constexpr int DEC_TILE = 32;      // anchor positions per CTA
+struct DecodeLevel {
+    const float* cls[8];
+    const float* reg;
+    const float* cor;
+    int w, hw;
+    int anchor_off;   // first anchor index of this level
+    int tile_off;     // first tile index of this level
+    float stride;
+};
+struct DecodeParams {
+    DecodeLevel lv[LP_MAX_LEVELS];
+    int n_levels;
+    int A;
+    float* out;
+};
+cudaError_t launch_decode(const DecodeParams& p, int n_tiles, int B, cudaStream_t stream);
+
+// ---- geometry.cu -------------------------------------------------------------------------------
+struct AnchorLevels {
+    int w[LP_MAX_LEVELS], hw[LP_MAX_LEVELS], off[LP_MAX_LEVELS];
+    float stride[LP_MAX_LEVELS];
+    int n_levels, A;
+    float offset;
+};
+cudaError_t launch_anchors(const AnchorLevels& lv, float* points, float* strides, cudaStream_t s);
+cudaError_t launch_dist2bbox(const float* d, const float* ap, long long n, int A, int xywh, float* out, cudaStream_t s);
+cudaError_t launch_dist2cor(const float* d, const float* ap, long long n, int A, float* out, cudaStream_t s);
+cudaError_t launch_xywh2xyxy(const float* in, long long n, long long is, float* out, long long os, cudaStream_t s);
+cudaError_t launch_rescale(float* rows, long long k, long long rs, float px, float py, float ratio, float w0, float h0,
+                           int do_round, cudaStream_t s);
+cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_det, const float* params, int do_round,
+                                 cudaStream_t s);
+
+}  // namespace lp

@@ -1,0 +1,165 @@
+"""Detect-head inference decode and its geometry helpers on B200.
+
+Drop-in surfaces (same names / argument meaning as the reference):
+  ``generate_anchors``  yolov6/assigners/anchor_generator.py:4   (eval, anchor-free branch :11-31)
+  ``dist2bbox``         yolov6/utils/general.py:29-40
+  ``dist2cor``          yolov6/utils/general.py:51-66
+  ``detect_decode``     the eval tail of ``Detect.forward``, effidehead.py:247-301
+  ``detect_forward_eval`` / ``DetectEval``  the whole eval branch (:214-301): the module's own
+                        convs (cuDNN, untouched) followed by the fused decode kernel.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _abi
+
+CLS_NAMES = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5")
+CLS_WIDTH = (31, 24, 37, 37, 37, 37, 37, 37)
+ROW = _abi.ROW
+
+
+def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RuntimeError(f"yolo_lp_b200: {what} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def generate_anchors(feats, fpn_strides, grid_cell_size=5.0, grid_cell_offset=0.5, device='cpu', is_eval=False,
+                     mode='af'):
+    """Generate anchors from features (reference signature).  Only the inference
+    branch (``is_eval=True, mode='af'``) is on the hot path and implemented here;
+    the training branch stays with the reference."""
+    assert feats is not None
+    if not is_eval or mode != 'af':
+        raise NotImplementedError("yolo_lp_b200.generate_anchors covers is_eval=True, mode='af' only")
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("yolo_lp_b200.generate_anchors needs a CUDA device (no CPU fallback)")
+    n = len(fpn_strides)
+    hs = (ctypes.c_int * n)(*[int(feats[i].shape[2]) for i in range(n)])
+    ws = (ctypes.c_int * n)(*[int(feats[i].shape[3]) for i in range(n)])
+    ss = (ctypes.c_float * n)(*[float(s) for s in fpn_strides])
+    A = sum(h * w for h, w in zip(hs, ws))
+    points = torch.empty((A, 2), dtype=torch.float32, device=device)
+    strides = torch.empty((A, 1), dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        _abi.call("lp_generate_anchors_f32", hs, ws, ss, n, float(grid_cell_offset), points.data_ptr(),
+                  strides.data_ptr(), _stream(device))
+    return points, strides
+
+
+def _broadcast_anchor_args(distance, anchor_points, width):
+    d = _cuda_f32(distance, "distance")
+    ap = _cuda_f32(anchor_points, "anchor_points")
+    if d.shape[-1] != width or ap.dim() != 2 or ap.shape[1] != 2 or d.dim() < 2 or d.shape[-2] != ap.shape[0]:
+        raise ValueError(f"expected distance [..., A, {width}] and anchor_points [A, 2], got "
+                         f"{tuple(distance.shape)} and {tuple(anchor_points.shape)}")
+    A = ap.shape[0]
+    return d, ap, d.numel() // (A * width), A
+
+
+def dist2bbox(distance, anchor_points, box_format='xyxy'):
+    '''Transform distance(ltrb) to box(xywh or xyxy).'''
+    if box_format not in ('xyxy', 'xywh'):
+        raise ValueError(box_format)
+    d, ap, n, A = _broadcast_anchor_args(distance, anchor_points, 4)
+    out = torch.empty_like(d)
+    with torch.cuda.device(d.device):
+        _abi.call("lp_dist2bbox_f32", d.data_ptr(), ap.data_ptr(), n, A, int(box_format == 'xywh'),
+                  out.data_ptr(), _stream(d.device))
+    return out
+
+
+def dist2cor(distance, anchor_points):
+    '''Transform 8 corner distances to the four corner points (TL, BL, BR, TR).'''
+    d, ap, n, A = _broadcast_anchor_args(distance, anchor_points, 8)
+    out = torch.empty_like(d)
+    with torch.cuda.device(d.device):
+        _abi.call("lp_dist2cor_f32", d.data_ptr(), ap.data_ptr(), n, A, out.data_ptr(), _stream(d.device))
+    return out
+
+
+def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None) -> torch.Tensor:
+    """Eval tail of ``Detect.forward`` (effidehead.py:247-301, ``use_dfl=False``).
+
+    ``levels``: per FPN level a dict of the raw prediction-conv outputs (NCHW, CUDA fp32):
+    ``pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w] reg[B,4,h,w] cor[B,8,h,w]``.
+    Returns the head tensor ``[B, A, 290]``.
+    """
+    n = len(levels)
+    if not 0 < n <= _abi.MAX_LEVELS or len(strides) != n:
+        raise ValueError("1..4 levels with one stride each")
+    arr = (_abi.LpLevel * n)()
+    keep = []  # keep contiguous copies alive until the launch is queued
+    B = int(levels[0]["reg"].shape[0])
+    device = levels[0]["reg"].device
+    A = 0
+    for i, (lv, s) in enumerate(zip(levels, strides)):
+        reg = _cuda_f32(lv["reg"], "reg")
+        _, c, h, w = reg.shape
+        if c != 4:
+            raise ValueError("reg must have 4 channels (use_dfl=False, reg_max=0)")
+        cor = _cuda_f32(lv["cor"], "cor")
+        if tuple(cor.shape) != (B, 8, h, w):
+            raise ValueError(f"cor shape {tuple(cor.shape)}")
+        keep += [reg, cor]
+        for g, (name, width) in enumerate(zip(CLS_NAMES, CLS_WIDTH)):
+            t = _cuda_f32(lv[name], name)
+            if tuple(t.shape) != (B, width, h, w):
+                raise ValueError(f"{name} shape {tuple(t.shape)} != {(B, width, h, w)}")
+            keep.append(t)
+            arr[i].cls[g] = t.data_ptr()
+        arr[i].reg, arr[i].cor = reg.data_ptr(), cor.data_ptr()
+        arr[i].h, arr[i].w, arr[i].stride = h, w, float(s)
+        A += h * w
+    if out is None:
+        out = torch.empty((B, A, ROW), dtype=torch.float32, device=device)
+    elif tuple(out.shape) != (B, A, ROW) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous fp32 [B, A, 290] tensor")
+    with torch.cuda.device(device):
+        _abi.call("lp_detect_decode_f32", arr, n, B, out.data_ptr(), _stream(device))
+    return out
+
+
+_PRED_ATTRS = tuple(n + "_preds" for n in CLS_NAMES)
+
+
+def detect_forward_eval(detect, x):
+    """Eval branch of the reference ``Detect.forward`` (effidehead.py:214-301) for a module
+    with the reference's attribute names: the stem / cls / reg / prediction convs run as they
+    are (torch + cuDNN), everything after them is one fused kernel."""
+    if getattr(detect, "use_dfl", False):
+        raise NotImplementedError("use_dfl=True (distillation heads) is outside the LP configs")
+    levels = []
+    for i in range(detect.nl):
+        f = detect.stems[i](x[i])
+        cls_feat = detect.cls_convs[i](f)
+        reg_feat = detect.reg_convs[i](f)
+        lv = {name: getattr(detect, attr)[i](cls_feat) for name, attr in zip(CLS_NAMES, _PRED_ATTRS)}
+        lv["reg"] = detect.reg_preds[i](reg_feat)
+        lv["cor"] = detect.cor_preds[i](reg_feat)
+        levels.append(lv)
+    return detect_decode(levels, [float(s) for s in detect.stride])
+
+
+class DetectEval(torch.nn.Module):
+    """Wraps a reference ``Detect`` module: training mode defers to it, eval mode runs
+    :func:`detect_forward_eval`."""
+
+    def __init__(self, detect):
+        super().__init__()
+        self.detect = detect
+
+    def forward(self, x):
+        if self.training:
+            return self.detect(x)
+        return detect_forward_eval(self.detect, x)

@@ -1,0 +1,171 @@
+"""Drop-in ``non_max_suppression`` (``yolov6/utils/nms.py:31-130``) on B200.
+
+Same signature, defaults and return type as the reference:
+``list`` of ``B`` fp32 tensors ``[k_b, 28]`` on ``prediction.device``, rows =
+``xyxy | 8 corner coords | 8 group confidences | 8 group argmax (as float)``,
+ordered by decreasing mean score (ties: ascending anchor).  All arithmetic runs
+in ``liblpnms.so`` (K1 filter + K2 sort/NMS/gather); PyTorch only owns the
+buffers and the stream.
+
+Deliberate differences from the reference:
+  * ``prediction`` is NOT mutated (reference: ``x[:,13:] *= x[:,4:5]``, nms.py:76);
+  * no 10 s wall-clock ``time_limit`` early exit (nms.py:63,126-128);
+  * with more than 30 000 candidates the cut is (score desc, anchor asc) where the
+    reference's unstable argsort is implementation-defined (nms.py:115-116).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _abi
+
+ROW, OUT, MAX_NMS = _abi.ROW, _abi.OUT, _abi.MAX_NMS
+
+
+def _check_thresholds(conf_thres, iou_thres):
+    # nms.py:57-58, same messages
+    assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
+    assert 0 <= iou_thres <= 1, f'iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided.'
+
+
+class NmsPlan:
+    """Pre-allocated buffers for repeated NMS calls of one shape on one device.
+
+    ``run`` only enqueues work on the current stream (memset + 2 kernel launches)
+    and returns device tensors; nothing synchronises.
+    """
+
+    KERNELS_PER_CALL = 2  # lp::filter_kernel, lp::nms_kernel
+
+    def __init__(self, B: int, A: int, max_det: int = 300, device=None, max_nms: int = MAX_NMS,
+                 want_anchor: bool = False):
+        _abi.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("yolo_lp_b200 runs on CUDA devices only (no CPU fallback)")
+        self.B, self.A, self.max_det, self.max_nms = int(B), int(A), int(max_det), int(max_nms)
+        nbytes = _abi.nms_workspace_bytes(self.B, self.A, self.max_det)
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.out = torch.empty((self.B, self.max_det, OUT), dtype=torch.float32, device=self.device)
+        self.counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+        self.kept_anchor = (torch.empty((self.B, self.max_det), dtype=torch.int32, device=self.device)
+                            if want_anchor else None)
+
+    def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, rescale: torch.Tensor | None = None,
+            do_round: bool = False, out=None, counts=None):
+        """Enqueue filter + NMS over ``pred[B,A,290]`` (CUDA, fp32, contiguous)."""
+        if pred.device != self.device or pred.dtype != torch.float32 or not pred.is_contiguous():
+            raise ValueError("pred must be a contiguous fp32 tensor on the plan's device")
+        if tuple(pred.shape) != (self.B, self.A, ROW):
+            raise ValueError(f"pred shape {tuple(pred.shape)} != {(self.B, self.A, ROW)}")
+        out = self.out if out is None else out
+        counts = self.counts if counts is None else counts
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _abi.call("lp_nms_f32", pred.data_ptr(), self.B, self.A, float(conf_thres), float(iou_thres),
+                      self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
+                      out.data_ptr(), counts.data_ptr(),
+                      self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), stream)
+        return out, counts
+
+    def run_filter(self, pred: torch.Tensor, conf_thres: float):
+        """Stage K1 only (lp_nms_filter_f32): candidates + counts are left in the workspace."""
+        with torch.cuda.device(self.device):
+            _abi.call("lp_nms_filter_f32", pred.data_ptr(), self.B, self.A, float(conf_thres),
+                      self.workspace.data_ptr(), self.workspace.numel(),
+                      torch.cuda.current_stream(self.device).cuda_stream)
+
+    def run_suppress(self, pred: torch.Tensor, iou_thres: float, rescale=None, do_round=False, out=None, counts=None):
+        """Stage K2 only (lp_nms_suppress_f32) on what :meth:`run_filter` left behind."""
+        out = self.out if out is None else out
+        counts = self.counts if counts is None else counts
+        with torch.cuda.device(self.device):
+            _abi.call("lp_nms_suppress_f32", pred.data_ptr(), self.B, self.A, float(iou_thres), self.max_det,
+                      self.max_nms, self.workspace.data_ptr(), self.workspace.numel(), out.data_ptr(),
+                      counts.data_ptr(), self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)),
+                      torch.cuda.current_stream(self.device).cuda_stream)
+        return out, counts
+
+    def candidate_counts(self) -> torch.Tensor:
+        """Per-image candidate counts K1 left in the workspace (device int32 view)."""
+        return self.workspace[: 4 * self.B].view(torch.int32)
+
+
+_plans: dict = {}
+
+
+def _plan_for(B, A, max_det, device, want_anchor=False) -> NmsPlan:
+    key = (B, A, max_det, device.index, torch.cuda.current_stream(device).cuda_stream, want_anchor)
+    plan = _plans.get(key)
+    if plan is None:
+        if len(_plans) > 16:
+            _plans.clear()
+        plan = _plans[key] = NmsPlan(B, A, max_det, device, want_anchor=want_anchor)
+    return plan
+
+
+def _device_input(prediction: torch.Tensor) -> torch.Tensor:
+    p = prediction
+    if p.dtype != torch.float32:
+        p = p.float()
+    if not p.is_contiguous() or p.data_ptr() % 16:
+        p = p.contiguous()
+        if p.data_ptr() % 16:
+            p = p.clone()
+    return p
+
+
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                        multi_label=False, max_det=300):
+    """Runs Non-Maximum Suppression on inference results (reference signature).
+
+    ``classes``, ``agnostic`` and ``multi_label`` are accepted and ignored, as in
+    the reference.  A CPU ``prediction`` is streamed to
+    the current CUDA device in chunks (H2D overlapped with the kernels) and the
+    detections come back as CPU tensors.
+    """
+    _check_thresholds(conf_thres, iou_thres)
+    if prediction.dim() != 3 or prediction.shape[2] != ROW:
+        raise ValueError(f"prediction must be [B, A, {ROW}], got {tuple(prediction.shape)}")
+    B, A, _ = prediction.shape
+    if B == 0:
+        return []
+    if A == 0 or max_det <= 0:
+        return [torch.zeros((0, OUT), device=prediction.device)] * B
+    if prediction.device.type == "cpu":
+        from .host import host_pipeline
+        return host_pipeline(B, A, max_det).run(prediction, conf_thres, iou_thres)
+    pred = _device_input(prediction)
+    plan = _plan_for(B, A, int(max_det), pred.device)
+    out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
+    _, counts = plan.run(pred, conf_thres, iou_thres, out=out)
+    ks = counts.cpu().tolist()  # the one host sync of the call
+    return [out[b, :k] for b, k in enumerate(ks)]
+
+
+def non_max_suppression_with_index(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300):
+    """Like :func:`non_max_suppression` but also returns the anchor index of every kept row
+    (test / debugging aid; CUDA input only)."""
+    _check_thresholds(conf_thres, iou_thres)
+    pred = _device_input(prediction)
+    B, A, _ = pred.shape
+    plan = _plan_for(B, A, int(max_det), pred.device, want_anchor=True)
+    out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
+    _, counts = plan.run(pred, conf_thres, iou_thres, out=out)
+    ks = counts.cpu().tolist()
+    idx = plan.kept_anchor.clone()
+    return [out[b, :k] for b, k in enumerate(ks)], [idx[b, :k].long() for b, k in enumerate(ks)]
+
+
+def xywh2xyxy(x):
+    """``yolov6/utils/nms.py:21-28`` for a CUDA tensor ``[n, 4]`` (any row stride)."""
+    if not isinstance(x, torch.Tensor) or x.device.type != "cuda":
+        raise RuntimeError("yolo_lp_b200.xywh2xyxy needs a CUDA tensor (no CPU fallback)")
+    src = x if (x.dtype == torch.float32 and x.stride(-1) == 1) else x.float().contiguous()
+    y = torch.empty((src.shape[0], 4), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        _abi.call("lp_xywh2xyxy_f32", src.data_ptr(), src.shape[0], src.stride(0), y.data_ptr(), 4,
+                  torch.cuda.current_stream(src.device).cuda_stream)
+    return y
