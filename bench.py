@@ -1,0 +1,331 @@
+#!/usr/bin/env python3
+"""Benchmark of the YOLO-LP post-processing hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
+
+A "step" is one pass of the hot path -- confidence filter + sort + greedy NMS + output
+rows (``lp_nms_f32``: K1 ``lp::filter_kernel`` + K2 ``lp::nms_kernel``) -- over one batch of
+synthetic head tensors ``[B, A, 290]`` that is already resident in HBM.  Workload at N=1 is
+BASELINE.json configs[1] (YOLO-LP-s 640x640, batch 32, conf 0.25 / IoU 0.45, max_det 300);
+N>1 is weak scaling, every rank owning its own 32-image shard of a 32*N-image batch with no
+collective on the data path (N=8 is configs[2]'s 256-image batch).
+
+One JSON line is printed by rank 0 with
+  value          images/s over all ranks, device-timed (CUDA events), max over ranks
+  e2e            the same metric through the public API ``non_max_suppression`` with HOST
+                 buffers: H2D of the head tensor from pinned memory and D2H of the detections
+                 are inside the timed region
+  roofline       K1's algorithmic bytes / its CUDA-event time vs the measured HBM peak
+  cpu_baseline   the torch-CPU port of the reference (oracle/torch_port.py) on this host
+``--impl reference`` times only that CPU port (the reference itself is not on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "post-proc images/sec"
+UNIT = "images/s"
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+CPU_CHUNK = 8                      # reference is driven in <= 8-image chunks (its 10 s time_limit)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (1-5) used as the per-GPU workload")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (default: min(steps, 20))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(cid: int):
+    from yolo_lp_b200 import synth
+    cfg = dict(synth.CONFIGS[cid])
+    name = {1: "cfg1 YOLO-LP-s 640x640 batch 1", 2: "cfg2 YOLO-LP-s 640x640 batch 32",
+            3: "cfg3 YOLO-LP-n 640x640 batch 256", 4: "cfg4 eval stress 640x640 batch 64 conf 0.001",
+            5: "cfg5 dense-plate 1280x1280 batch 32"}[cid]
+    return cfg, name
+
+
+def config_block(cfg, name, n_gpus, B_local):
+    return {"workload": name, "images_per_gpu": B_local, "global_batch": B_local * n_gpus, "anchors": cfg["A"],
+            "row_floats": 290, "conf_thres": cfg["conf"], "iou_thres": cfg["iou"], "max_det": cfg["max_det"],
+            "sharding": f"images x{n_gpus}, no collective",
+            "l2": "input %.1f MB per GPU > 126 MB L2 (no flush needed)" % (B_local * cfg["A"] * 1160 / 1e6)}
+
+
+# --------------------------------------------------------------------------------------------- CPU arm
+def cpu_pass(pred, cfg):
+    """One pass of the reference's CPU path over the sample, <= CPU_CHUNK images per call;
+    the input is cloned outside the timed region because the port mutates it like nms.py:76."""
+    import torch
+    from oracle import torch_port
+    chunks = [pred[s:s + CPU_CHUNK].clone() for s in range(0, pred.shape[0], CPU_CHUNK)]
+    t0 = time.perf_counter()
+    n = 0
+    for c in chunks:
+        out = torch_port.non_max_suppression(c, cfg["conf"], cfg["iou"], max_det=cfg["max_det"])
+        n += len(out)
+    return time.perf_counter() - t0, n
+
+
+def cpu_sample(cfg, budget_images):
+    from yolo_lp_b200 import synth
+    B = min(cfg["B"], budget_images)
+    return synth.synth_head(B, cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"])
+
+
+def cpu_sample_size(cid):
+    # ~10 ms/img normal, ~0.5 s/img dense, ~0.13 s/img at 1280^2 on 8 cores
+    return {1: 1, 2: 32, 3: 32, 4: 4, 5: 8}[cid]
+
+
+def run_reference_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, name = workload(args.config)
+    pred = cpu_sample(cfg, cpu_sample_size(args.config))
+    for _ in range(max(1, args.warmup)):
+        cpu_pass(pred, cfg)
+    times = []
+    for _ in range(args.steps):
+        dt, _n = cpu_pass(pred, cfg)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = pred.shape[0] / (ms / 1e3)
+    sample = f"{pred.shape[0]} images of {name} per step, {CPU_CHUNK}-image calls, torch CPU port of nms.py + torchvision.ops.nms"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(cfg, name, args.gpus, cfg["B"]),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while a timed region runs."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _once(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                self.nv, "nvmlDeviceGetCurrentClocksEventReasons") else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._once()
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.ok:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.ok:
+            self._once()
+            self._stop.set()
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def visible_to_physical(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except Exception:
+            return local_index
+    return local_index
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from yolo_lp_b200 import synth
+    from yolo_lp_b200.nms import NmsPlan, non_max_suppression
+    from yolo_lp_b200.host import host_pipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:   # launched bare: re-exec under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
+            sys.exit(subprocess.call(cmd))
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: yolo_lp_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, name = workload(args.config)
+    B = cfg["B"] if args.config != 3 else 32      # per-GPU shard; config 3 is the 8-GPU aggregate of config 2's shape
+    first = rank * B                               # this rank's contiguous image range of the global batch
+    host_pred = synth.synth_head(B, cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"],
+                                 first_index=first, pin_memory=True)
+    pred = host_pred.to(dev)
+    plan = NmsPlan(B, cfg["A"], cfg["max_det"], dev)
+    conf, iou = cfg["conf"], cfg["iou"]
+    K, W = args.steps, max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg: K steps of (K1, K2), events round every stage
+    for _ in range(W):
+        plan.run(pred, conf, iou)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    clocks = ClockSampler(visible_to_physical(local))
+    barrier()
+    with clocks:
+        t_begin.record()
+        for k in range(K):
+            ev[k][0].record()
+            plan.run_filter(pred, conf)
+            ev[k][1].record()
+            plan.run_suppress(pred, iou)
+            ev[k][2].record()
+        t_end.record()
+        barrier()
+    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
+    ms_per_step = total_ms / K
+    filt_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
+    nms_ms = [ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]
+    step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(K)]
+    counts = plan.counts.cpu()
+    cand = plan.candidate_counts().cpu()
+    value = world * B / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (K1): algorithmic bytes = every row read once + 8 B per survivor
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    algo_bytes = B * cfg["A"] * 1160 + int(cand.sum()) * 8
+    filt_avg = sum(filt_ms) / K
+    achieved = algo_bytes / (filt_avg * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"cfg{args.config}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"kernel": "lp::filter_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": filt_avg,
+                "share_of_step": filt_avg / (sum(step_ms) / K)}
+
+    # ---- end-to-end leg: public API on a pinned HOST tensor; H2D + kernels + D2H per step
+    Ke = args.e2e_steps or max(3, min(K, 20))
+    pipe = host_pipeline(B, cfg["A"], cfg["max_det"])
+    for _ in range(3):
+        res = non_max_suppression(host_pred, conf, iou, max_det=cfg["max_det"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        res = non_max_suppression(host_pred, conf, iou, max_det=cfg["max_det"])
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / Ke
+    assert [int(r.shape[0]) for r in res] == counts.tolist(), "host-buffer path disagrees with the device path"
+    e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": Ke,
+           "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "api": "yolo_lp_b200.non_max_suppression(cpu pinned tensor) -> lp_nms_f32 per 48 MiB chunk"}
+    barrier()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_block(cfg, name, world, B),
+                "p50_batch_latency_ms": statistics.median(step_ms), "p95_batch_latency_ms": sorted(step_ms)[int(0.95 * (K - 1))],
+                "stage_ms": {"filter_avg": filt_avg, "nms_avg": sum(nms_ms) / K},
+                "detections_per_image": sum(counts.tolist()) / B, "candidates_per_image": float(cand.sum()) / B,
+                "roofline": roofline, "e2e": e2e, "clocks": clocks.summary(),
+                "gpu_launches": K * NmsPlan.KERNELS_PER_CALL}
+        if world == 1 and not args.no_cpu_baseline:
+            sample = cpu_sample(cfg, cpu_sample_size(args.config))
+            cpu_pass(sample, cfg)                      # warm-up
+            spent, images, passes = 0.0, 0, 0
+            while spent < 10.0 and passes < 50:
+                dt, n = cpu_pass(sample, cfg)
+                spent, images, passes = spent + dt, images + n, passes + 1
+            line["cpu_baseline"] = {
+                "value": images / spent, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "host_cpus": os.cpu_count(),
+                "sample": f"{passes} passes over {sample.shape[0]} images of {name} ({spent:.1f} s), "
+                          f"{CPU_CHUNK}-image calls, torch CPU port of nms.py + torchvision.ops.nms"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
