@@ -109,6 +109,10 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
                                void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                const float* rescale, int do_round, lp_stream_t stream);
 
+/* Debug only (process-global, not thread-safe): device buffer [B,8] of int64 that K2 fills with
+ * clock64() stamps at its phase boundaries; NULL switches it off. */
+LP_API int lp_debug_nms_timing(long long* buf);
+
 /* Detect.forward eval tail: raw per-level conv outputs -> out[B,A,290],
  * A = sum h*w, levels in order; anchors are computed from the index, never
  * materialised. */

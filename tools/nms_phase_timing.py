@@ -1,0 +1,37 @@
+#!/usr/bin/env python3
+"""Per-phase clock64 breakdown of K2 (lp::nms_kernel) for one BASELINE config (debug aid).
+
+    python tools/nms_phase_timing.py [config id]
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from yolo_lp_b200 import _abi, synth
+from yolo_lp_b200.nms import NmsPlan
+
+cid = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+cfg = synth.CONFIGS[cid]
+B = min(cfg["B"], 32)
+dev = torch.device("cuda:0")
+pred = synth.synth_head(B, cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"]).to(dev)
+plan = NmsPlan(B, cfg["A"], cfg["max_det"], dev)
+buf = torch.zeros((B, 16), dtype=torch.int64, device=dev)
+for _ in range(3):
+    plan.run(pred, cfg["conf"], cfg["iou"])
+_abi.call("lp_debug_nms_timing", buf.data_ptr())
+plan.run(pred, cfg["conf"], cfg["iou"])
+torch.cuda.synchronize()
+_abi.call("lp_debug_nms_timing", None)
+t = buf.cpu()
+names = ["(unused)", "sort", "window0-load", "nms", "gather"]
+t[:, 1] = t[:, 0]
+d = (t[:, 1:6] - t[:, 0:5]).double()
+print(f"cfg{cid}: B={B}  candidates/img={plan.candidate_counts().float().mean().item():.0f}  kept/img={plan.counts.float().mean().item():.0f}")
+for i, n in enumerate(names):
+    print(f"  {n:14s} mean {d[:, i].mean():9.0f} clk   max {d[:, i].max():9.0f} clk")
+g1 = (t[:, 6] - t[:, 4]).double()
+print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk")
+tot = (t[:, 5] - t[:, 0]).double()
+print(f"  total          mean {tot.mean():9.0f} clk   max {tot.max():9.0f} clk   (SM clock ~1.9 GHz -> {tot.max() / 1.9e3:.1f} us)")

@@ -85,6 +85,14 @@ LP_API int lp_nms_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) 
     return LP_OK;
 }
 
+// Debug hook (not part of the product ABI, not thread-safe): when set, K2 writes clock64 stamps
+// of its phases for every image into buf[B][8].  Used by tools/nms_phase_timing.py only.
+static long long* g_debug_timing = nullptr;
+LP_API int lp_debug_nms_timing(long long* buf) {
+    g_debug_timing = buf;
+    return LP_OK;
+}
+
 // shared validation + parameter setup of the two NMS stages
 static int nms_setup(const float* pred, int B, int A, int max_det, void* workspace, size_t workspace_bytes,
                      FilterParams& f, NmsParams& n) {
@@ -118,6 +126,7 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.rescale = nullptr;
     n.do_round = 0;
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
+    n.timing = g_debug_timing;
     return LP_OK;
 }
 

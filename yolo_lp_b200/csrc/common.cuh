@@ -68,6 +68,9 @@ __device__ __forceinline__ bool iou_exceeds(const float4& a, float area_a, const
     const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
     const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
     const float inter = __fmul_rn(w, h);
+    // inter is +0 for disjoint boxes (the common case): 0/u is 0, -0 or NaN, never > thr (thr >= 0),
+    // so the IEEE division -- whose zero-numerator case runs the slow path -- is skipped exactly.
+    if (!(inter > 0.0f)) return false;
     const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
     return ovr > thr_floor;
 }

@@ -35,6 +35,7 @@ struct NmsParams {
     const float* rescale;       // [B, 5] or null
     int do_round;
     int sort_smem_keys;         // capacity of the shared-memory sort buffer (power of two)
+    long long* timing;          // debug only: [B, 8] clock64 stamps per phase, or null
 };
 cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
 int nms_sort_smem_keys(unsigned A);

@@ -72,214 +72,275 @@ __device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned t_ac
     }
 }
 
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// bits i of a 32-bit chunk mask with i % R == rep (R replicas share the members of a chunk)
+__device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
+    unsigned m = 0;
+    for (unsigned i = rep; i < 32; i += R) m |= 1u << i;
+    return m;
+}
+
 __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // [sort_smem_keys]
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // sort buffer, later row staging
     __shared__ float4 wbox[NMS_THREADS];      // boxes of the current window
     __shared__ float4 kbox[KEPT_SMEM];        // first KEPT_SMEM kept boxes
     __shared__ int kanchor[KEPT_SMEM];        // and their anchors
+    __shared__ unsigned s_sh[NMS_THREADS];    // per candidate: members of the current chunk that suppress it
+    __shared__ unsigned rank_sh[RANK_SORT_MAX];
     __shared__ unsigned words[NMS_WARPS];     // alive bitmask of the window, one word per chunk
-    __shared__ unsigned kmask;                // kept mask of the chunk being resolved
     __shared__ int s_nkeep;
 
     const unsigned b = blockIdx.x;
-    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned tid = threadIdx.x, lane = tid & 31;
     const float* pred = p.pred + (size_t)b * p.A * ROW;
     float4* kept_box = p.kept_box + (size_t)b * p.max_det;
     int* kept_anchor = p.kept_anchor_ws + (size_t)b * p.max_det;
 
+#define LP_STAMP(i) do { if (p.timing != nullptr && tid == 0) p.timing[(size_t)b * 16 + (i)] = clock64(); } while (0)
+    LP_STAMP(0);
     unsigned N = (unsigned)p.counts[b];
     if (N > p.A) N = p.A;
     if (tid < NMS_WARPS) words[tid] = 0;
     if (tid == 0) s_nkeep = 0;
     __syncthreads();
 
-    // threads that own a candidate in a window; the others go straight to the gather
+    // t_act threads own one candidate of a window each; when the candidate set is small the
+    // spare threads work as R-1 replicas of the owners (P = R * t_act threads take part in the
+    // sort and NMS barriers), the rest wait for the gather.
     const unsigned t_act = N >= NMS_THREADS ? NMS_THREADS : ((N + 31u) & ~31u);
-    if (tid < t_act && p.max_det > 0) {
+    const unsigned R = t_act ? NMS_THREADS / t_act : 1u, P = R * t_act;
+
+    if (tid < P && p.max_det > 0) {
+        const unsigned j = tid % t_act, rep = tid / t_act;  // candidate slot, replica id (warp-uniform)
+        const unsigned cw = j >> 5;                           // chunk of the slot
+        const bool owner = rep == 0;
         int n_keep = 0;
         // ------------------------------------------------------------------ sort
         unsigned long long* gkeys = p.keys + (size_t)b * p.key_stride;
         const unsigned long long* sorted;
         bool sorted_global = false;
         if (N <= RANK_SORT_MAX) {
-            // rank sort: keys are distinct (they embed the anchor), rank = number of smaller keys
-            unsigned long long key = ~0ull;
-            if (tid < N) key = __ldcg(gkeys + tid);
-            skeys[tid] = key;
-            bar_active(t_act);
+            // rank sort: keys are distinct (they embed the anchor), rank = number of smaller keys;
+            // replica `rep` counts over its slice of the keys, two per 128-bit shared-memory load
+            if (owner) {
+                skeys[j] = j < N ? __ldcg(gkeys + j) : ~0ull;  // ~0 is never smaller than a real key
+                rank_sh[j] = 0;
+            }
+            bar_active(P);
+            const unsigned long long key = skeys[j];
+            const unsigned pairs = (t_act / 2 + R - 1) / R;
+            const unsigned p0 = rep * pairs, p1 = min(p0 + pairs, t_act / 2);
+            const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(skeys);
             unsigned rank = 0;
 #pragma unroll 4
-            for (unsigned i = 0; i < N; ++i) rank += skeys[i] < key;
-            if (tid < N) skeys[RANK_SORT_MAX + rank] = key;
-            bar_active(t_act);
+            for (unsigned i = p0; i < p1; ++i) {
+                const ulonglong2 kk = kp[i];
+                rank += (kk.x < key) + (kk.y < key);
+            }
+            atomicAdd(&rank_sh[j], rank);
+            bar_active(P);
+            if (owner && j < N) skeys[RANK_SORT_MAX + rank_sh[j]] = key;
             sorted = skeys + RANK_SORT_MAX;
         } else {
             const unsigned npad = next_pow2(N);
             if (npad <= (unsigned)p.sort_smem_keys) {
-                for (unsigned i = tid; i < npad; i += t_act) skeys[i] = i < N ? __ldcg(gkeys + i) : ~0ull;
-                bar_active(t_act);
-                bitonic_sort<false>(skeys, npad, t_act);
+                for (unsigned i = tid; i < npad; i += P) skeys[i] = i < N ? __ldcg(gkeys + i) : ~0ull;
+                bar_active(P);
+                bitonic_sort<false>(skeys, npad, P);
                 sorted = skeys;
             } else {  // key_stride >= npad is guaranteed by lp_nms_workspace_bytes
-                for (unsigned i = N + tid; i < npad; i += t_act) __stcg(gkeys + i, ~0ull);
-                bar_active(t_act);
-                bitonic_sort<true>(gkeys, npad, t_act);
+                for (unsigned i = N + tid; i < npad; i += P) __stcg(gkeys + i, ~0ull);
+                bar_active(P);
+                bitonic_sort<true>(gkeys, npad, P);
                 sorted = gkeys;
                 sorted_global = true;
             }
         }
         if (N > (unsigned)p.max_nms) N = p.max_nms;  // nms.py:115-116
+        bar_active(P);
+        LP_STAMP(2);  // sorted
 
         // ------------------------------------------------------------------ windowed, chunked greedy NMS
         const unsigned lower = (1u << lane) - 1u;
+        const unsigned my_members = replica_mask(R, rep);
         for (unsigned w0 = 0; w0 < N && n_keep < p.max_det; w0 += NMS_THREADS) {
-            const unsigned pos = w0 + tid;
-            bool alive = pos < N;
             unsigned anchor = 0;
-            float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-            float area = 0.f;
-            if (alive) {
-                anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
-                const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
-                const float2 c = __ldg(r), s = __ldg(r + 1);
-                box = xywh_to_xyxy(c.x, c.y, s.x, s.y);  // nms.py:79
-                area = box_area(box);
-            }
-            wbox[tid] = box;
-            // suppression by boxes kept in earlier windows
-            for (int k = 0; k < n_keep; ++k) {
-                const float4 kb = k < KEPT_SMEM ? kbox[k] : __ldcg(kept_box + k);
-                if (alive && iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) alive = false;
-            }
-            {
+            if (owner) {
+                const unsigned pos = w0 + j;
+                bool alive = pos < N;
+                float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (alive) {
+                    anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
+                    const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
+                    const float2 c = __ldg(r), s = __ldg(r + 1);
+                    box = xywh_to_xyxy(c.x, c.y, s.x, s.y);  // nms.py:79
+                }
+                wbox[j] = box;
+                s_sh[j] = 0;
+                // suppression by boxes kept in earlier windows (only reached with N > 1024, R == 1)
+                const float area = box_area(box);
+                for (int k = 0; k < n_keep; ++k) {
+                    const float4 kb = k < KEPT_SMEM ? kbox[k] : __ldcg(kept_box + k);
+                    if (alive && iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) alive = false;
+                }
                 const unsigned word = __ballot_sync(0xffffffffu, alive);
-                if (lane == 0) words[warp] = word;
+                if (lane == 0) words[cw] = word;
             }
-            bar_active(t_act);
+            bar_active(P);
+            if (w0 == 0) LP_STAMP(3);  // first window loaded
+            const float4 box = wbox[j];
+            const float area = box_area(box);
 
             int c = -1;
             while (true) {
-                // next chunk (warp) that still has alive members; every warp computes it redundantly
+                // next chunk that still has alive members; every warp computes it redundantly
                 const unsigned wl = (int)lane > c ? words[lane] : 0u;
                 const unsigned nz = __ballot_sync(0xffffffffu, wl != 0);
                 if (!nz) break;
+                const bool alive = (words[cw] >> lane) & 1u;
                 c = __ffs(nz) - 1;
                 const unsigned A = __shfl_sync(0xffffffffu, wl, c);
-                // S: members of chunk c that suppress this thread's candidate if they are kept
-                unsigned S = 0;
-                if ((int)warp >= c && alive) {
+                // S: members of chunk c that suppress this thread's candidate if they are kept;
+                // every replica looks at its share of the alive members
+                if ((int)cw >= c && alive) {
                     const float4* cb = wbox + c * 32;
-                    for (unsigned m = A; m; m &= m - 1) {
-                        const int i = __ffs(m) - 1;
-                        const float4 kb = cb[i];
-                        if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= 1u << i;
+                    unsigned S = 0;
+                    // four members per round: independent IoU chains (ILP); the trip count depends
+                    // only on A and the replica, so it is warp-uniform
+                    for (unsigned m = A & my_members; m;) {
+                        int idx[4];
+                        unsigned bit[4];
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            idx[r] = m ? __ffs(m) - 1 : 0;
+                            bit[r] = m & (0u - m);  // lowest set bit, 0 once the share is exhausted
+                            m &= m - 1;
+                        }
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const float4 kb = cb[idx[r]];
+                            if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= bit[r];
+                        }
                     }
-                    if ((int)warp == c) S &= lower;  // only earlier members of the own chunk count
+                    if ((int)cw == c) S &= lower;  // only earlier members of the own chunk count
+                    if (S) atomicOr(&s_sh[j], S);
                 }
-                if ((int)warp == c) {
-                    // greedy inside the chunk: K_j = A_j and no kept earlier member suppresses j.
-                    // Iterating K <- F(K) fixes one more leading member per round; the unique
-                    // fixed point is the sequential result.
+                bar_active(P);
+                // greedy inside the chunk, computed redundantly by every warp: K_i = A_i and no kept
+                // earlier member suppresses i.  Iterating K <- F(K) fixes one more leading member per
+                // round; the unique fixed point is the sequential result.
+                unsigned K = A;
+                {
+                    const unsigned sc = s_sh[c * 32 + lane];
                     const bool in_a = (A >> lane) & 1u;
-                    unsigned K = A;
                     while (true) {
-                        const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (S & K) == 0);
+                        const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);
                         if (K2 == K) break;
                         K = K2;
                     }
                     const int room = p.max_det - n_keep;
                     if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
-                    if ((K >> lane) & 1u) {
-                        const int k = n_keep + __popc(K & lower);
-                        if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
-                        kept_box[k] = box;
-                        kept_anchor[k] = (int)anchor;
-                        const char* row = reinterpret_cast<const char*>(pred + (size_t)anchor * ROW);
-#pragma unroll
-                        for (int l = 0; l < ROW * 4; l += 128) prefetch_l2(row + l);  // for the gather
+                }
+                if (owner) {
+                    if ((int)cw == c) {
+                        if ((K >> lane) & 1u) {
+                            const int k = n_keep + __popc(K & lower);
+                            if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
+                            else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
+                        }
+                        if (lane == 0) words[cw] = 0;  // every member is now kept or suppressed
+                    } else if ((int)cw > c) {
+                        bool still = alive;
+                        if (alive) {
+                            const unsigned S = s_sh[j];
+                            if (S) s_sh[j] = 0;
+                            still = (S & K) == 0;
+                        }
+                        const unsigned word = __ballot_sync(0xffffffffu, still);
+                        if (lane == 0) words[cw] = word;
                     }
-                    if (lane == 0) kmask = K;
                 }
-                bar_active(t_act);
-                const unsigned K = kmask;
                 n_keep += __popc(K);
-                if ((S & K) != 0 || (int)warp == c) alive = false;
                 if (n_keep >= p.max_det) break;
-                if ((int)warp > c) {
-                    const unsigned word = __ballot_sync(0xffffffffu, alive);
-                    if (lane == 0) words[warp] = word;
-                }
-                bar_active(t_act);
+                bar_active(P);
             }
-            bar_active(t_act);  // kbox / kept_* visible, wbox / words / kmask free for the next window
+            bar_active(P);  // kbox / kept_* visible, wbox / words / s_sh free for the next window
         }
         if (tid == 0) s_nkeep = n_keep;
+        LP_STAMP(4);  // NMS done
     }
     __syncthreads();
 
     // ---------------------------------------------------------------------- gather
+    // Kept rows are staged in shared memory (cp.async, 8-byte granules: rows are only 8-byte
+    // aligned), then one thread per (row, group) scans its <= 37 class scores in order -- strict
+    // '>' keeps the first maximum like torch.max on CPU -- and one thread per (row, coordinate)
+    // emits the box / corner columns.
     const int n_keep = s_nkeep;
     if (tid == 0) p.out_counts[b] = n_keep;
-    float pad_x = 0.f, pad_y = 0.f, ratio = 1.f, w0f = 0.f, h0f = 0.f;
+    float* srow = reinterpret_cast<float*>(smem_raw);
+    const int cap_rows = (int)(((size_t)p.sort_smem_keys * sizeof(unsigned long long)) / (ROW * 4));
     const bool do_rescale = p.rescale != nullptr;
+    float pad_x = 0.f, pad_y = 0.f, ratio = 1.f, w0f = 0.f, h0f = 0.f;
     if (do_rescale) {
         const float* rp = p.rescale + (size_t)b * 5;
         pad_x = rp[0]; pad_y = rp[1]; ratio = rp[2]; w0f = rp[3]; h0f = rp[4];
     }
-    const unsigned hl = tid & 15;  // lane inside the half-warp that owns a row
-    for (int k0 = 2 * warp; k0 < n_keep; k0 += NMS_THREADS / 16) {  // warp-uniform trip count (shuffles inside)
-        const bool live = k0 + (int)(lane >> 4) < n_keep;
-        const int k = live ? k0 + (int)(lane >> 4) : k0;  // an idle upper half-warp mirrors the lower one, stores masked
-        const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
-        const float* row = pred + (size_t)anchor * ROW;
-        // issue every load of the row before the first use: one memory round trip per row
-        const float obj = __ldg(row + 4);
-        const float corner = (hl >= 4 && hl < 12) ? __ldg(row + hl + 1) : 0.f;  // cols 5..12 -> out 4..11
-        float v[NGROUP][3];
-#pragma unroll
-        for (int g = 0; g < NGROUP; ++g) {
+    for (int base = 0; base < n_keep; base += cap_rows) {
+        const int nb = min(cap_rows, n_keep - base);
+        for (int i = tid; i < nb * (ROW / 2); i += NMS_THREADS) {
+            const int r = i / (ROW / 2), q = i - r * (ROW / 2);
+            const int k = base + r;
+            const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+            cp_async_8(srow + r * ROW + 2 * q, pred + (size_t)anchor * ROW + 2 * q);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (base == 0) LP_STAMP(6);  // rows staged
+        for (int t = tid; t < nb * NGROUP; t += NMS_THREADS) {
+            const int r = t >> 3, g = t & 7;
+            const float* row = srow + r * ROW;
+            const float obj = row[4];
             const int s = group_begin(g), e = group_begin(g + 1);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) v[g][q] = (s + 16 * q + (int)hl < e) ? __ldg(row + s + 16 * q + hl) : 0.f;
-        }
-        const float4 bx = k < KEPT_SMEM ? kbox[k] : kept_box[k];
-        float o0 = hl == 0 ? bx.x : hl == 1 ? bx.y : hl == 2 ? bx.z : hl == 3 ? bx.w : corner;  // out[hl]
-        float o1 = 0.f;                                                                           // out[16 + hl]
-#pragma unroll
-        for (int g = 0; g < NGROUP; ++g) {
-            constexpr int kInvalid = 1 << 20;
-            const int s = group_begin(g), e = group_begin(g + 1);
-            float best = -INFINITY;
-            int bi = kInvalid;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {  // widths 31 / 24 / 37: at most three columns per lane
-                if (s + 16 * q + (int)hl < e) {
-                    const float x = __fmul_rn(v[g][q], obj);  // nms.py:76
-                    if (x > best) { best = x; bi = 16 * q + hl; }
-                }
+            float best = __fmul_rn(row[s], obj);  // nms.py:76
+            int bi = 0;
+            for (int i = s + 1; i < e; ++i) {
+                const float x = __fmul_rn(row[i], obj);
+                if (x > best) { best = x; bi = i - s; }
             }
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {  // max, ties -> lowest index (torch.max on CPU)
-                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            float* dst = p.out + ((size_t)b * p.max_det + base + r) * OUTW;
+            dst[12 + g] = best;
+            dst[20 + g] = (float)bi;
+        }
+        for (int t = tid; t < nb * 12; t += NMS_THREADS) {
+            const int r = t / 12, c = t - r * 12;
+            const int k = base + r;
+            float val;
+            if (c < 4) {
+                const float4 bx = k < KEPT_SMEM ? kbox[k] : kept_box[k];
+                val = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : bx.w;
+            } else {
+                val = srow[r * ROW + c + 1];  // corners: columns 5..12 -> output 4..11 (nms.py:94)
             }
-            if ((int)hl == 12 + g) o0 = best;            // out 12..15 = conf 0..3
-            if ((int)hl == g - 4) o1 = best;             // out 16..19 = conf 4..7
-            if ((int)hl == 4 + g) o1 = (float)bi;        // out 20..27 = argmax 0..7
+            if (do_rescale)
+                val = (c & 1) ? rescale_coord(val, pad_y, ratio, h0f, p.do_round) : rescale_coord(val, pad_x, ratio, w0f, p.do_round);
+            p.out[((size_t)b * p.max_det + k) * OUTW + c] = val;
         }
-        if (do_rescale && hl < 12) {
-            o0 = (hl & 1) ? rescale_coord(o0, pad_y, ratio, h0f, p.do_round)
-                          : rescale_coord(o0, pad_x, ratio, w0f, p.do_round);
-        }
-        if (live) {
-            float* dst = p.out + ((size_t)b * p.max_det + k) * OUTW;
-            dst[hl] = o0;
-            if (hl < 12) dst[16 + hl] = o1;
-            if (p.kept_anchor != nullptr && hl == 0) p.kept_anchor[(size_t)b * p.max_det + k] = anchor;
-        }
+        if (p.kept_anchor != nullptr)
+            for (int t = tid; t < nb; t += NMS_THREADS) {
+                const int k = base + t;
+                p.kept_anchor[(size_t)b * p.max_det + k] = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+            }
+        __syncthreads();
     }
+    LP_STAMP(5);  // gather done
+#undef LP_STAMP
 }
 
 cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream) {
@@ -292,9 +353,8 @@ cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream) {
 }
 
 int nms_sort_smem_keys(unsigned A) {
-    unsigned n = 2 * RANK_SORT_MAX;  // the rank sort needs an input and an output buffer
-    while (n < A && n < (unsigned)SORT_SMEM_KEYS) n <<= 1;
-    return (int)n;
+    (void)A;  // always the full buffer: it doubles as the row staging area of the gather
+    return SORT_SMEM_KEYS;
 }
 
 }  // namespace lp
