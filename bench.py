@@ -192,7 +192,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from yolo_lp_b200 import synth
-    from yolo_lp_b200.nms import NmsPlan, non_max_suppression
+    from yolo_lp_b200.nms import NmsPipeline, NmsPlan, non_max_suppression
     from yolo_lp_b200.host import host_pipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,31 +233,50 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident leg: K steps of (K1, K2), events round every stage
+    # ---- device-resident leg (headline): K steps through the two-stream pipeline -- K1 (filter) of
+    # step k+1 overlaps K2 (sort/NMS/gather) of step k; CUDA events round every K1 launch
+    pipe = NmsPipeline(B, cfg["A"], cfg["max_det"], dev)
+    pipe.start()
     for _ in range(W):
-        plan.run(pred, conf, iou)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        pipe.submit(pred, conf, iou)
+    pipe.finish()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(visible_to_physical(local))
     barrier()
     with clocks:
         t_begin.record()
+        pipe.start()
         for k in range(K):
-            ev[k][0].record()
-            plan.run_filter(pred, conf)
-            ev[k][1].record()
-            plan.run_suppress(pred, iou)
-            ev[k][2].record()
+            pipe.submit(pred, conf, iou, timing=ev[k])
+        pipe.finish()
         t_end.record()
         barrier()
     total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
     ms_per_step = total_ms / K
     filt_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]
-    nms_ms = [ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]
-    step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(K)]
-    counts = plan.counts.cpu()
-    cand = plan.candidate_counts().cpu()
+    counts = pipe.plans[0].counts.cpu()
+    assert all(torch.equal(pl.counts.cpu(), counts) for pl in pipe.plans)
     value = world * B / (ms_per_step / 1e3)
+
+    # ---- latency leg: the same K1, K2 strictly one after the other on one stream (no overlap)
+    Kl = min(K, 100)
+    for _ in range(W):
+        plan.run(pred, conf, iou)
+    lv = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Kl)]
+    barrier()
+    for k in range(Kl):
+        lv[k][0].record()
+        plan.run_filter(pred, conf)
+        lv[k][1].record()
+        plan.run_suppress(pred, iou)
+        lv[k][2].record()
+    barrier()
+    step_ms = [lv[k][0].elapsed_time(lv[k][2]) for k in range(Kl)]
+    lat_filter = sum(lv[k][0].elapsed_time(lv[k][1]) for k in range(Kl)) / Kl
+    lat_nms = sum(lv[k][1].elapsed_time(lv[k][2]) for k in range(Kl)) / Kl
+    assert torch.equal(plan.counts.cpu(), counts), "pipelined and serial paths disagree"
+    cand = plan.candidate_counts().cpu()
 
     # ---- roofline of the dominant kernel (K1): algorithmic bytes = every row read once + 8 B per survivor
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -278,7 +297,8 @@ def run_ours(args):
     roofline = {"kernel": "lp::filter_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": filt_avg,
-                "share_of_step": filt_avg / (sum(step_ms) / K)}
+                "share_of_step": filt_avg / ms_per_step,
+                "note": "K1 timed inside the pipelined region (K2 of the previous step running concurrently)"}
 
     # ---- end-to-end leg: public API on a pinned HOST tensor; H2D + kernels + D2H per step
     Ke = args.e2e_steps or max(3, min(K, 20))
@@ -301,8 +321,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_block(cfg, name, world, B),
-                "p50_batch_latency_ms": statistics.median(step_ms), "p95_batch_latency_ms": sorted(step_ms)[int(0.95 * (K - 1))],
-                "stage_ms": {"filter_avg": filt_avg, "nms_avg": sum(nms_ms) / K},
+                "pipeline": "2 streams, depth 2: K1 of step k+1 overlaps K2 of step k",
+                "p50_batch_latency_ms": statistics.median(step_ms), "p95_batch_latency_ms": sorted(step_ms)[int(0.95 * (Kl - 1))],
+                "serial_stage_ms": {"filter_avg": lat_filter, "nms_avg": lat_nms},
                 "detections_per_image": sum(counts.tolist()) / B, "candidates_per_image": float(cand.sum()) / B,
                 "roofline": roofline, "e2e": e2e, "clocks": clocks.summary(),
                 "gpu_launches": K * NmsPlan.KERNELS_PER_CALL}

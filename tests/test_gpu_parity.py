@@ -320,3 +320,40 @@ def test_detect_forward_eval_runs_module_convs_then_kernel():
     want = lp_oracle.detect_decode(levels, (8, 16, 32))
     assert tuple(out.shape) == (2, 315, 290)
     np.testing.assert_allclose(out.cpu().numpy(), want, rtol=1e-5, atol=0)
+
+
+# ------------------------------------------------------------------ two-stream pipeline
+def test_pipeline_matches_serial_path_on_alternating_batches():
+    """K1 of batch i+1 overlapping K2 of batch i must not change any result: two different
+    batches are submitted alternately through the depth-2 pipeline and compared with the oracle."""
+    from yolo_lp_b200.nms import NmsPipeline
+    preds = [synth.synth_head(6, 2100, 320, 8, 120, seed=s) for s in (51, 52, 53)]
+    wants = [lp_oracle.non_max_suppression(p.numpy(), 0.15, 0.5) for p in preds]
+    devs = [p.to(DEV) for p in preds]
+    pipe = NmsPipeline(6, 2100, 300, torch.device(DEV))
+    pipe.start()
+    results = []
+    for i in range(9):
+        slot, out, counts = pipe.submit(devs[i % 3], 0.15, 0.5)
+        pipe.done[slot].synchronize()          # this batch's results are final once its K2 is done
+        results.append((i % 3, out.clone(), counts.clone()))
+    pipe.finish()
+    torch.cuda.synchronize()
+    for which, out, counts in results:
+        for b, k in enumerate(counts.cpu().tolist()):
+            assert_rows_equal(out[b, :k].cpu().numpy(), wants[which][b], f"pipeline batch {which}[{b}]")
+
+
+def test_filter_cta_limit_does_not_change_results():
+    from yolo_lp_b200 import _abi
+    pred = synth.synth_head(3, 8400, 640, 24, 300, seed=61)
+    want = lp_oracle.non_max_suppression(pred.numpy(), 0.25, 0.45)
+    dev = pred.to(DEV)
+    try:
+        for ctas in (1, 7, 148, 0):
+            _abi.call("lp_tune", 0, ctas)
+            got = lp.non_max_suppression(dev, 0.25, 0.45)
+            for b in range(3):
+                assert_rows_equal(got[b].cpu().numpy(), want[b], f"ctas={ctas}[{b}]")
+    finally:
+        _abi.call("lp_tune", 0, 0)

@@ -30,7 +30,7 @@ struct WsLayout {
 static WsLayout ws_layout(int B, int A, int max_det) {
     WsLayout w;
     size_t off = 0;
-    w.counts = off;      off = align_up(off + sizeof(int) * (size_t)B);
+    w.counts = off;      off = align_up(off + sizeof(int) * ((size_t)B + 1));  // + the tile counter of K1
     w.keys = off;        off = align_up(off + sizeof(unsigned long long) * (size_t)B * key_stride_for(A));
     w.kept_box = off;    off = align_up(off + sizeof(float4) * (size_t)B * (size_t)max_det);
     w.kept_anchor = off; off = align_up(off + sizeof(int) * (size_t)B * (size_t)max_det);
@@ -93,6 +93,18 @@ LP_API int lp_debug_nms_timing(long long* buf) {
     return LP_OK;
 }
 
+// Tuning hook (process-global, not thread-safe; defaults are right for production): key 0 = upper
+// bound on the CTAs of K1 (0 = one per SM).  Leaving some SMs to K2 lets the NMS of batch i overlap
+// the filter of batch i+1 when the two stages are driven from two streams.
+static int g_filter_cta_limit = 0;
+LP_API int lp_tune(int key, int value) {
+    if (key == 0 && value >= 0) {
+        g_filter_cta_limit = value;
+        return LP_OK;
+    }
+    return LP_E_ARG;
+}
+
 // shared validation + parameter setup of the two NMS stages
 static int nms_setup(const float* pred, int B, int A, int max_det, void* workspace, size_t workspace_bytes,
                      FilterParams& f, NmsParams& n) {
@@ -110,6 +122,7 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     f.keys = reinterpret_cast<unsigned long long*>(ws + w.keys);
     f.counts = reinterpret_cast<int*>(ws + w.counts);
     f.key_stride = key_stride_for((unsigned)A);
+    f.tile_counter = reinterpret_cast<unsigned*>(f.counts + B);
     n.pred = pred;
     n.A = (unsigned)A;
     n.keys = f.keys;
@@ -141,10 +154,16 @@ LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres,
     const WsLayout w = ws_layout(B, A, 0);
     if (workspace_bytes < w.kept_box) return LP_E_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * (size_t)B, s);
+    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);  // counts + tile counter
     if (e != cudaSuccess) return (int)e;
     f.conf = (float)conf_thres;  // tensor >= python-scalar compares in fp32
-    return (int)launch_filter(f, num_sms_cached(), s);
+    // K1 saturates HBM with roughly half the SMs (one 217 KB CTA each); the rest is left free so
+    // that K2 of the previous batch (one CTA per image, driven from a second stream) can run
+    // concurrently instead of queueing behind K1's persistent CTAs.
+    int ctas = num_sms_cached();
+    ctas -= B < ctas / 2 ? B : ctas / 2;
+    if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < num_sms_cached() ? g_filter_cta_limit : num_sms_cached();
+    return (int)launch_filter(f, ctas, s);
 }
 
 LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,

@@ -48,14 +48,22 @@ __global__ void __launch_bounds__(FILTER_THREADS, 1) filter_kernel(const FilterP
     float* buf = reinterpret_cast<float*>(smem + warp * TILE_BYTES);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + FILTER_WARPS * TILE_BYTES) + warp;
 
-    const unsigned stride = gridDim.x * FILTER_WARPS;
+    // Tile scheduling: the first tile of every warp is static (its global warp id), all later
+    // ones are claimed from a global counter, one claim ahead of use so the atomic's round trip
+    // hides behind the load in flight.  Dynamic claims keep every SM busy until the last tile and
+    // let late-starting CTAs (SMs still occupied by the previous batch's K2) simply take less.
+    const unsigned n_warps = gridDim.x * FILTER_WARPS;
     unsigned tile = blockIdx.x * FILTER_WARPS + warp;
+    unsigned next = 0xffffffffu;
     uint64_t policy = 0;
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
         policy = l2_evict_first_policy();
-        if (tile < p.n_tiles) issue_tile(p, tile, buf, bar, policy);
+        if (tile < p.n_tiles) {
+            issue_tile(p, tile, buf, bar, policy);
+            next = n_warps + atomicAdd(p.tile_counter, 1u);
+        }
     }
     __syncwarp();
 
@@ -85,10 +93,12 @@ __global__ void __launch_bounds__(FILTER_THREADS, 1) filter_kernel(const FilterP
         }
         // all lanes have consumed the stage: hand it back to the async proxy and refill
         __syncwarp();
-        const unsigned next = tile + stride;
+        next = __shfl_sync(0xffffffffu, next, 0);
+        unsigned claim = 0xffffffffu;
         if (lane == 0 && next < p.n_tiles) {
             fence_proxy_async_smem();
             issue_tile(p, next, buf, bar, policy);
+            claim = n_warps + atomicAdd(p.tile_counter, 1u);
         }
 
         const bool pass = valid && (filt >= p.conf);
@@ -109,6 +119,7 @@ __global__ void __launch_bounds__(FILTER_THREADS, 1) filter_kernel(const FilterP
             todo &= ~grp;
         }
         tile = next;
+        next = claim;
     }
 }
 

@@ -14,6 +14,7 @@ struct FilterParams {
     unsigned long long* keys;     // [B, key_stride]
     int* counts;                  // [B], zeroed before launch
     unsigned key_stride;
+    unsigned* tile_counter;       // dynamic tile scheduler, zeroed before launch
 };
 cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t stream);
 

@@ -1,36 +1,44 @@
-// K2 -- per-image sort -> exact greedy NMS -> fused gather (+ optional rescale/round).
+// K2 -- per-image order-by-score -> exact greedy NMS -> fused gather (+ optional rescale/round).
 //
 // One 1024-thread CTA per image; images are independent (nms.py:68 loop body), so a batch is
-// B concurrent CTAs and the stage's latency is that of the slowest image.  Only the warps that
-// own candidates take part in the sort/NMS barriers (named barrier over `t_act` threads).
+// B concurrent CTAs and the stage's latency is that of the slowest image.
 //
-//   sort    keys (score desc, anchor asc) from K1: rank sort (<= 512 keys), bitonic in shared
-//           memory (<= 16384 keys) or bitonic in the global workspace beyond that.  Ascending key
-//           order reproduces torchvision's stable descending sort over the anchor-ordered
-//           compaction (nms.py:97,121); more than max_nms candidates are cut to the first
-//           max_nms (nms.py:115-116).
+//   order   keys (score desc, anchor asc) from K1.  Ascending key order reproduces torchvision's
+//           stable descending sort over the anchor-ordered compaction (nms.py:97,121); more than
+//           max_nms candidates are cut to the first max_nms (nms.py:115-116).
+//             N <= 1024   rank sort in shared memory (rank = number of smaller keys)
+//             N <= 2048   bitonic sort in shared memory
+//             larger      SEGMENTED: a 1024-bin histogram over the score bits splits the candidates
+//                         into score-ordered segments of >= 512 keys; only the segments the greedy
+//                         walk actually reaches are compacted and sorted (with max_det = 300 that is
+//                         usually the first one or two).  A pathological histogram (one bin holding nearly
+//                         everything, e.g. all scores equal) falls back to a full bitonic sort, in
+//                         shared memory up to 16384 keys and in the global workspace beyond.
 //   NMS     torchvision.ops.nms CPU semantics (call site nms.py:121), bit-exact fp32 IoU, evaluated
-//           lazily and chunk-wise: the sorted list is walked in 1024-wide windows (one candidate
-//           per thread); a window is first tested against every box kept so far, then resolved
-//           32 candidates (one warp's chunk) at a time -- every later candidate collects the
-//           bitmask S of chunk members that would suppress it, the chunk's own warp settles which
-//           members are kept with a ballot fixed-point (exactly the greedy order), and the kept
-//           mask K is broadcast: candidates with S & K die.  Serial depth is the number of
-//           non-empty chunks (<= N/32), not the number of kept boxes; IoU work is only done
-//           against still-alive chunk members, and everything stops as soon as max_det rows are
-//           kept, which the reference's truncation keep[:max_det] (nms.py:122-123) makes legal.
-//   gather  one half-warp per kept row re-reads the row from `pred` (prefetched into L2 when it
-//           was kept), recomputes nms.py:76-96 (group maxima with first-index argmax, xyxy box,
-//           corners) and writes the 28-float output row, optionally mapped back to source
-//           coordinates (inferer.py:203-228, :100).
+//           lazily and chunk-wise: the ordered list is walked in 512-wide windows (one owner thread
+//           per candidate, the other threads act as replicas that share the IoU work); a window is
+//           first tested against every box kept so far, then resolved 32 candidates (one chunk) at
+//           a time -- every later candidate collects the bitmask S of chunk members that would
+//           suppress it, the kept members K of the chunk are settled with a ballot fixed point
+//           (exactly the greedy order) and candidates with S & K die.  Serial depth is the number of
+//           non-empty chunks, IoU work is only done against still-alive members, and everything
+//           stops as soon as max_det rows are kept, which the reference's truncation keep[:max_det]
+//           (nms.py:122-123) makes legal.
+//   gather  kept rows are staged in shared memory, one thread per (row, group) recomputes
+//           nms.py:76-96 (group maxima with first-index argmax), one per (row, coordinate) emits the
+//           xyxy box and the corners, optionally mapped back to source coordinates
+//           (inferer.py:203-228, :100).
 #include "kernels.cuh"
 
 namespace lp {
 
 constexpr int NMS_THREADS = 1024;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int SORT_SMEM_KEYS = 16384;  // 128 KB
-constexpr int RANK_SORT_MAX = 512;     // rank sort needs 2 * RANK_SORT_MAX keys of shared memory
+constexpr int WIN = 512;               // candidates per window
+constexpr int SORT_SMEM_KEYS = 16384;  // 128 KB sort buffer (later the row staging area)
+constexpr int RANK_SORT_MAX = 1024;    // rank sort: input keys [0, n), output keys [RANK_SORT_MAX, RANK_SORT_MAX + n)
+constexpr int DIRECT_SORT_MAX = 2048;  // up to here everything is sorted at once
+constexpr int HIST_BINS = 1024;
+constexpr int SEG_TARGET = 512;        // minimum candidates per segment
 constexpr int KEPT_SMEM = 1024;        // kept boxes / anchors cached in shared memory (rest via L2)
 
 __device__ __forceinline__ unsigned next_pow2(unsigned n) { return n <= 1 ? 1u : 1u << (32 - __clz(n - 1)); }
@@ -38,14 +46,12 @@ __device__ __forceinline__ unsigned next_pow2(unsigned n) { return n <= 1 ? 1u :
 // barrier over the first `nthreads` threads of the CTA (a multiple of 32); id 1, id 0 is __syncthreads
 __device__ __forceinline__ void bar_active(unsigned nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // In-place ascending bitonic sort of n (power of two) keys; `keys` is shared or global memory.
 template <bool kGlobal>
-__device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned t_act) {
+__device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned nthreads) {
     for (unsigned k = 2; k <= n; k <<= 1) {
         for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned t = threadIdx.x; t < (n >> 1); t += t_act) {
+            for (unsigned t = threadIdx.x; t < (n >> 1); t += nthreads) {
                 const unsigned i = 2 * t - (t & (j - 1));  // bit j of i is clear
                 const unsigned l = i | j;
                 unsigned long long a, b;
@@ -67,7 +73,7 @@ __device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned t_ac
                     }
                 }
             }
-            bar_active(t_act);
+            bar_active(nthreads);
         }
     }
 }
@@ -78,6 +84,50 @@ __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
+// (a < b) as 0/1 through the borrow of a 64-bit subtraction: 3 integer instructions
+__device__ __forceinline__ unsigned lt_u64(unsigned long long a, unsigned long long b) {
+    unsigned r;
+    asm("{\n\t.reg .u32 t;\n\t"
+        "sub.cc.u32 t, %1, %3;\n\t"
+        "subc.cc.u32 t, %2, %4;\n\t"
+        "subc.u32 %0, 0, 0;\n\t}"
+        : "=r"(r)
+        : "r"((unsigned)a), "r"((unsigned)(a >> 32)), "r"((unsigned)b), "r"((unsigned)(b >> 32)));
+    return r & 1u;  // 0 - 0 - borrow = 0xffffffff when a < b
+}
+
+// Rank sort of n <= RANK_SORT_MAX distinct keys (they embed the anchor) by the first `nthreads`
+// threads: rank = number of smaller keys.  Keys sit in keys[0, n); the sorted list is written to
+// keys[RANK_SORT_MAX, RANK_SORT_MAX + n).  The n^2 comparisons are spread over all threads: slot
+// jj of replica rr counts over the rr-th slice of the keys, two per 128-bit shared-memory load, and
+// the partial ranks are summed in `acc`.  Every one of the `nthreads` threads must call this.
+__device__ void rank_sort(unsigned long long* keys, unsigned* acc, unsigned n, unsigned nthreads) {
+    const unsigned tid = threadIdx.x;
+    const unsigned wn = (n + 31u) & ~31u;            // slots, padded with ~0 (never smaller than a key)
+    const unsigned rn = nthreads / wn, jj = tid % wn, rr = tid / wn;
+    const bool work = rr < rn;
+    for (unsigned i = n + tid; i < wn; i += nthreads) keys[i] = ~0ull;
+    if (tid < wn) acc[tid] = 0;
+    bar_active(nthreads);
+    unsigned long long key = 0;
+    if (work) {
+        key = keys[jj];
+        const unsigned pairs = (wn / 2 + rn - 1) / rn;
+        const unsigned p0 = rr * pairs, p1 = min(p0 + pairs, wn / 2);
+        const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(keys);
+        unsigned rank = 0;
+#pragma unroll 4
+        for (unsigned i = p0; i < p1; ++i) {
+            const ulonglong2 kk = kp[i];
+            rank += lt_u64(kk.x, key) + lt_u64(kk.y, key);
+        }
+        atomicAdd(&acc[jj], rank);
+    }
+    bar_active(nthreads);
+    if (work && rr == 0 && jj < n) keys[RANK_SORT_MAX + acc[jj]] = key;
+    bar_active(nthreads);
+}
+
 // bits i of a 32-bit chunk mask with i % R == rep (R replicas share the members of a chunk)
 __device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
     unsigned m = 0;
@@ -88,12 +138,15 @@ __device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
 __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // sort buffer, later row staging
-    __shared__ float4 wbox[NMS_THREADS];      // boxes of the current window
+    __shared__ float4 wbox[WIN];              // boxes of the current window
     __shared__ float4 kbox[KEPT_SMEM];        // first KEPT_SMEM kept boxes
     __shared__ int kanchor[KEPT_SMEM];        // and their anchors
-    __shared__ unsigned s_sh[NMS_THREADS];    // per candidate: members of the current chunk that suppress it
-    __shared__ unsigned rank_sh[RANK_SORT_MAX];
-    __shared__ unsigned words[NMS_WARPS];     // alive bitmask of the window, one word per chunk
+    __shared__ unsigned s_sh[WIN];            // per candidate: members of the current chunk that suppress it
+    __shared__ unsigned scratch[HIST_BINS];   // score histogram (inclusive scan), lives across segments
+    __shared__ unsigned rank_acc[RANK_SORT_MAX];  // rank-sort partial ranks
+    __shared__ unsigned words[32];            // alive bitmask of the window, one word per chunk
+    __shared__ unsigned red[32];              // cross-warp reductions
+    __shared__ unsigned s_misc[4];            // [0] segment end bin, [1] segment fill counter
     __shared__ int s_nkeep;
 
     const unsigned b = blockIdx.x;
@@ -106,171 +159,266 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     LP_STAMP(0);
     unsigned N = (unsigned)p.counts[b];
     if (N > p.A) N = p.A;
-    if (tid < NMS_WARPS) words[tid] = 0;
+    if (tid < 32) words[tid] = 0;
     if (tid == 0) s_nkeep = 0;
     __syncthreads();
 
-    // t_act threads own one candidate of a window each; when the candidate set is small the
-    // spare threads work as R-1 replicas of the owners (P = R * t_act threads take part in the
-    // sort and NMS barriers), the rest wait for the gather.
-    const unsigned t_act = N >= NMS_THREADS ? NMS_THREADS : ((N + 31u) & ~31u);
-    const unsigned R = t_act ? NMS_THREADS / t_act : 1u, P = R * t_act;
+    // W owner threads hold one candidate of a window each; the spare threads work as R-1 replicas
+    // of the owners (P = R * W threads take part in the order/NMS barriers), the rest wait for the
+    // gather.  N >= 512: W = 512, R = 2, P = 1024.
+    const unsigned W = N >= WIN ? WIN : ((N + 31u) & ~31u);
+    const unsigned R = W ? NMS_THREADS / W : 1u, P = R * W;
 
     if (tid < P && p.max_det > 0) {
-        const unsigned j = tid % t_act, rep = tid / t_act;  // candidate slot, replica id (warp-uniform)
-        const unsigned cw = j >> 5;                           // chunk of the slot
+        const unsigned j = tid % W, rep = tid / W;  // candidate slot, replica id (warp-uniform)
+        const unsigned cw = j >> 5;                   // chunk of the slot
         const bool owner = rep == 0;
-        int n_keep = 0;
-        // ------------------------------------------------------------------ sort
         unsigned long long* gkeys = p.keys + (size_t)b * p.key_stride;
-        const unsigned long long* sorted;
-        bool sorted_global = false;
+        int n_keep = 0;
+
+        // ------------------------------------------------------------------ ordering mode
+        const unsigned long long* sorted = skeys;
+        bool sorted_global = false, segmented = false;
+        unsigned n_seg = N;         // candidates in the current (sorted) segment
+        unsigned kmin = 0, shift = 0;
         if (N <= RANK_SORT_MAX) {
-            // rank sort: keys are distinct (they embed the anchor), rank = number of smaller keys;
-            // replica `rep` counts over its slice of the keys, two per 128-bit shared-memory load
-            if (owner) {
-                skeys[j] = j < N ? __ldcg(gkeys + j) : ~0ull;  // ~0 is never smaller than a real key
-                rank_sh[j] = 0;
-            }
+            for (unsigned i = tid; i < N; i += P) skeys[i] = __ldcg(gkeys + i);
             bar_active(P);
-            const unsigned long long key = skeys[j];
-            const unsigned pairs = (t_act / 2 + R - 1) / R;
-            const unsigned p0 = rep * pairs, p1 = min(p0 + pairs, t_act / 2);
-            const ulonglong2* kp = reinterpret_cast<const ulonglong2*>(skeys);
-            unsigned rank = 0;
-#pragma unroll 4
-            for (unsigned i = p0; i < p1; ++i) {
-                const ulonglong2 kk = kp[i];
-                rank += (kk.x < key) + (kk.y < key);
-            }
-            atomicAdd(&rank_sh[j], rank);
-            bar_active(P);
-            if (owner && j < N) skeys[RANK_SORT_MAX + rank_sh[j]] = key;
+            rank_sort(skeys, rank_acc, N, P);
             sorted = skeys + RANK_SORT_MAX;
         } else {
-            const unsigned npad = next_pow2(N);
-            if (npad <= (unsigned)p.sort_smem_keys) {
-                for (unsigned i = tid; i < npad; i += P) skeys[i] = i < N ? __ldcg(gkeys + i) : ~0ull;
+            if (N > DIRECT_SORT_MAX) {
+                // ---- histogram of the score bits (upper key word); P == 1024 == HIST_BINS here
+                unsigned lo = 0xffffffffu, hi = 0;
+                for (unsigned i = tid; i < N; i += P) {
+                    const unsigned k = (unsigned)(__ldcg(gkeys + i) >> 32);
+                    lo = min(lo, k);
+                    hi = max(hi, k);
+                }
+                lo = __reduce_min_sync(0xffffffffu, lo);
+                hi = __reduce_max_sync(0xffffffffu, hi);
+                if (lane == 0) { red[tid >> 5] = lo; scratch[tid >> 5] = hi; }
                 bar_active(P);
-                bitonic_sort<false>(skeys, npad, P);
-                sorted = skeys;
-            } else {  // key_stride >= npad is guaranteed by lp_nms_workspace_bytes
-                for (unsigned i = N + tid; i < npad; i += P) __stcg(gkeys + i, ~0ull);
+                kmin = __reduce_min_sync(0xffffffffu, red[lane]);
+                const unsigned kmax = __reduce_max_sync(0xffffffffu, scratch[lane]);
+                const unsigned d = kmax - kmin;
+                shift = d < HIST_BINS ? 0 : (32 - __clz(d)) - 10;  // (d >> shift) < 1024, monotone in the key
                 bar_active(P);
-                bitonic_sort<true>(gkeys, npad, P);
-                sorted = gkeys;
-                sorted_global = true;
+                scratch[tid] = 0;
+                bar_active(P);
+                for (unsigned i = tid; i < N; i += P)
+                    atomicAdd(&scratch[((unsigned)(__ldcg(gkeys + i) >> 32) - kmin) >> shift], 1u);
+                bar_active(P);
+                // inclusive scan over the 1024 bins (one per thread)
+                const unsigned cnt = scratch[tid];
+                unsigned inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if ((int)lane >= o) inc += t;
+                }
+                if (lane == 31) red[tid >> 5] = inc;
+                const unsigned big = __reduce_max_sync(0xffffffffu, cnt);
+                bar_active(P);
+                unsigned wsum = red[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned t = __shfl_up_sync(0xffffffffu, wsum, o);
+                    if ((int)lane >= o) wsum += t;
+                }
+                const unsigned before = __shfl_sync(0xffffffffu, wsum, (tid >> 5) ? (tid >> 5) - 1 : 0);
+                inc += (tid >> 5) ? before : 0u;
+                bar_active(P);
+                scratch[tid] = inc;
+                if (lane == 0) red[tid >> 5] = big;
+                bar_active(P);
+                const unsigned biggest = __reduce_max_sync(0xffffffffu, red[lane]);
+                // a segment is the shortest run of bins reaching SEG_TARGET keys: it fits the sort
+                // buffer unless a single bin is huge
+                segmented = biggest <= (unsigned)(p.sort_smem_keys - SEG_TARGET - RANK_SORT_MAX);
+            }
+            if (!segmented) {
+                const unsigned npad = next_pow2(N);
+                if (npad <= (unsigned)p.sort_smem_keys) {
+                    for (unsigned i = tid; i < npad; i += P) skeys[i] = i < N ? __ldcg(gkeys + i) : ~0ull;
+                    bar_active(P);
+                    bitonic_sort<false>(skeys, npad, P);
+                } else {  // key_stride >= npad is guaranteed by lp_nms_workspace_bytes
+                    for (unsigned i = N + tid; i < npad; i += P) __stcg(gkeys + i, ~0ull);
+                    bar_active(P);
+                    bitonic_sort<true>(gkeys, npad, P);
+                    sorted = gkeys;
+                    sorted_global = true;
+                }
             }
         }
-        if (N > (unsigned)p.max_nms) N = p.max_nms;  // nms.py:115-116
         bar_active(P);
-        LP_STAMP(2);  // sorted
+        LP_STAMP(2);  // ordered (or histogram ready)
 
-        // ------------------------------------------------------------------ windowed, chunked greedy NMS
         const unsigned lower = (1u << lane) - 1u;
         const unsigned my_members = replica_mask(R, rep);
-        for (unsigned w0 = 0; w0 < N && n_keep < p.max_det; w0 += NMS_THREADS) {
-            unsigned anchor = 0;
-            if (owner) {
-                const unsigned pos = w0 + j;
-                bool alive = pos < N;
-                float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (alive) {
-                    anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
-                    const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
-                    const float2 c = __ldg(r), s = __ldg(r + 1);
-                    box = xywh_to_xyxy(c.x, c.y, s.x, s.y);  // nms.py:79
-                }
-                wbox[j] = box;
-                s_sh[j] = 0;
-                // suppression by boxes kept in earlier windows (only reached with N > 1024, R == 1)
-                const float area = box_area(box);
-                for (int k = 0; k < n_keep; ++k) {
-                    const float4 kb = k < KEPT_SMEM ? kbox[k] : __ldcg(kept_box + k);
-                    if (alive && iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) alive = false;
-                }
-                const unsigned word = __ballot_sync(0xffffffffu, alive);
-                if (lane == 0) words[cw] = word;
-            }
-            bar_active(P);
-            if (w0 == 0) LP_STAMP(3);  // first window loaded
-            const float4 box = wbox[j];
-            const float area = box_area(box);
-
-            int c = -1;
-            while (true) {
-                // next chunk that still has alive members; every warp computes it redundantly
-                const unsigned wl = (int)lane > c ? words[lane] : 0u;
-                const unsigned nz = __ballot_sync(0xffffffffu, wl != 0);
-                if (!nz) break;
-                const bool alive = (words[cw] >> lane) & 1u;
-                c = __ffs(nz) - 1;
-                const unsigned A = __shfl_sync(0xffffffffu, wl, c);
-                // S: members of chunk c that suppress this thread's candidate if they are kept;
-                // every replica looks at its share of the alive members
-                if ((int)cw >= c && alive) {
-                    const float4* cb = wbox + c * 32;
-                    unsigned S = 0;
-                    // four members per round: independent IoU chains (ILP); the trip count depends
-                    // only on A and the replica, so it is warp-uniform
-                    for (unsigned m = A & my_members; m;) {
-                        int idx[4];
-                        unsigned bit[4];
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            idx[r] = m ? __ffs(m) - 1 : 0;
-                            bit[r] = m & (0u - m);  // lowest set bit, 0 once the share is exhausted
-                            m &= m - 1;
-                        }
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const float4 kb = cb[idx[r]];
-                            if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= bit[r];
-                        }
+        const unsigned n_chunks = W >> 5;
+        unsigned consumed = 0;   // candidates of earlier segments
+        unsigned seg_bin0 = 0;   // first histogram bin of the next segment
+        bool first_window = true;
+        while (consumed < N && consumed < (unsigned)p.max_nms && n_keep < p.max_det) {
+            if (segmented) {
+                // ---- next segment: bins [seg_bin0, e] with e the first bin reaching SEG_TARGET keys
+                const unsigned base_cnt = seg_bin0 ? scratch[seg_bin0 - 1] : 0u;
+                if (tid == 0) { s_misc[0] = HIST_BINS - 1; s_misc[1] = 0; }
+                bar_active(P);
+                if (tid >= seg_bin0 && scratch[tid] - base_cnt >= (unsigned)SEG_TARGET) atomicMin(&s_misc[0], tid);
+                bar_active(P);
+                const unsigned e = s_misc[0];
+                n_seg = scratch[e] - base_cnt;
+                for (unsigned i0 = 0; i0 < N; i0 += P) {  // warp-aggregated compaction, order irrelevant
+                    const unsigned i = i0 + tid;
+                    unsigned long long key = 0;
+                    bool take = false;
+                    if (i < N) {
+                        key = __ldcg(gkeys + i);
+                        const unsigned bin = ((unsigned)(key >> 32) - kmin) >> shift;
+                        take = bin >= seg_bin0 && bin <= e;
                     }
-                    if ((int)cw == c) S &= lower;  // only earlier members of the own chunk count
-                    if (S) atomicOr(&s_sh[j], S);
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    unsigned base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&s_misc[1], (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) skeys[base + __popc(m & lower)] = key;
                 }
                 bar_active(P);
-                // greedy inside the chunk, computed redundantly by every warp: K_i = A_i and no kept
-                // earlier member suppresses i.  Iterating K <- F(K) fixes one more leading member per
-                // round; the unique fixed point is the sequential result.
-                unsigned K = A;
-                {
-                    const unsigned sc = s_sh[c * 32 + lane];
-                    const bool in_a = (A >> lane) & 1u;
-                    while (true) {
-                        const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);
-                        if (K2 == K) break;
-                        K = K2;
+                if (n_seg <= (unsigned)RANK_SORT_MAX) {
+                    rank_sort(skeys, rank_acc, n_seg, P);
+                    sorted = skeys + RANK_SORT_MAX;
+                } else {
+                    const unsigned npad = next_pow2(n_seg);
+                    for (unsigned i = n_seg + tid; i < npad; i += P) skeys[i] = ~0ull;
+                    bar_active(P);
+                    bitonic_sort<false>(skeys, npad, P);
+                    sorted = skeys;
+                }
+                seg_bin0 = e + 1;
+            }
+            const unsigned n_use = min(n_seg, (unsigned)p.max_nms - consumed);  // nms.py:115-116
+
+            // -------------------------------------------------------------- windows of the segment
+            for (unsigned w0 = 0; w0 < n_use && n_keep < p.max_det; w0 += W) {
+                unsigned anchor = 0;
+                bool valid = false;
+                if (owner) {
+                    const unsigned pos = w0 + j;
+                    valid = pos < n_use;
+                    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) {
+                        anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
+                        const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
+                        const float2 c = __ldg(r), s = __ldg(r + 1);
+                        bx = xywh_to_xyxy(c.x, c.y, s.x, s.y);  // nms.py:79
                     }
-                    const int room = p.max_det - n_keep;
-                    if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
+                    wbox[j] = bx;
+                    s_sh[j] = 0;
+                }
+                bar_active(P);
+                const float4 box = wbox[j];
+                const float area = box_area(box);
+                if (n_keep > 0) {
+                    // suppression by boxes kept in earlier windows / segments, shared by the replicas
+                    if (w0 + j < n_use) {
+                        bool hit = false;
+                        for (int k = (int)rep; k < n_keep; k += (int)R) {
+                            const float4 kb = k < KEPT_SMEM ? kbox[k] : __ldcg(kept_box + k);
+                            hit |= iou_exceeds(kb, box_area(kb), box, area, p.iou_floor);
+                        }
+                        if (hit) s_sh[j] = 1;
+                    }
+                    bar_active(P);
                 }
                 if (owner) {
-                    if ((int)cw == c) {
-                        if ((K >> lane) & 1u) {
-                            const int k = n_keep + __popc(K & lower);
-                            if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
-                            else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
-                        }
-                        if (lane == 0) words[cw] = 0;  // every member is now kept or suppressed
-                    } else if ((int)cw > c) {
-                        bool still = alive;
-                        if (alive) {
-                            const unsigned S = s_sh[j];
-                            if (S) s_sh[j] = 0;
-                            still = (S & K) == 0;
-                        }
-                        const unsigned word = __ballot_sync(0xffffffffu, still);
-                        if (lane == 0) words[cw] = word;
-                    }
+                    const bool alive = valid && s_sh[j] == 0;
+                    if (n_keep > 0) s_sh[j] = 0;
+                    const unsigned word = __ballot_sync(0xffffffffu, alive);
+                    if (lane == 0) words[cw] = word;
                 }
-                n_keep += __popc(K);
-                if (n_keep >= p.max_det) break;
                 bar_active(P);
+                if (first_window) { LP_STAMP(3); first_window = false; }  // first window loaded
+
+                int c = -1;
+                while (true) {
+                    // next chunk that still has alive members; every warp computes it redundantly
+                    const unsigned wl = ((int)lane > c && lane < n_chunks) ? words[lane] : 0u;
+                    const unsigned nz = __ballot_sync(0xffffffffu, wl != 0);
+                    if (!nz) break;
+                    const bool alive = (words[cw] >> lane) & 1u;
+                    c = __ffs(nz) - 1;
+                    const unsigned A = __shfl_sync(0xffffffffu, wl, c);
+                    // S: members of chunk c that suppress this thread's candidate if they are kept;
+                    // every replica looks at its share of the alive members
+                    if ((int)cw >= c && alive) {
+                        const float4* cb = wbox + c * 32;
+                        unsigned S = 0;
+                        // four members per round: independent IoU chains (ILP); the trip count
+                        // depends only on A and the replica, so it is warp-uniform
+                        for (unsigned m = A & my_members; m;) {
+                            int idx[4];
+                            unsigned bit[4];
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                idx[r] = m ? __ffs(m) - 1 : 0;
+                                bit[r] = m & (0u - m);  // lowest set bit, 0 once the share is exhausted
+                                m &= m - 1;
+                            }
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const float4 kb = cb[idx[r]];
+                                if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= bit[r];
+                            }
+                        }
+                        if ((int)cw == c) S &= lower;  // only earlier members of the own chunk count
+                        if (S) atomicOr(&s_sh[j], S);
+                    }
+                    bar_active(P);
+                    // greedy inside the chunk, computed redundantly by every warp: K_i = A_i and no
+                    // kept earlier member suppresses i.  Iterating K <- F(K) fixes one more leading
+                    // member per round; the unique fixed point is the sequential result.
+                    unsigned K = A;
+                    {
+                        const unsigned sc = s_sh[c * 32 + lane];
+                        const bool in_a = (A >> lane) & 1u;
+                        while (true) {
+                            const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);
+                            if (K2 == K) break;
+                            K = K2;
+                        }
+                        const int room = p.max_det - n_keep;
+                        if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
+                    }
+                    if (owner) {
+                        if ((int)cw == c) {
+                            if ((K >> lane) & 1u) {
+                                const int k = n_keep + __popc(K & lower);
+                                if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
+                                else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
+                            }
+                            if (lane == 0) words[cw] = 0;  // every member is now kept or suppressed
+                        } else if ((int)cw > c) {
+                            bool still = alive;
+                            if (alive) {
+                                const unsigned S = s_sh[j];
+                                if (S) s_sh[j] = 0;
+                                still = (S & K) == 0;
+                            }
+                            const unsigned word = __ballot_sync(0xffffffffu, still);
+                            if (lane == 0) words[cw] = word;
+                        }
+                    }
+                    n_keep += __popc(K);
+                    if (n_keep >= p.max_det) break;
+                    bar_active(P);
+                }
+                bar_active(P);  // kbox / kept_* visible, wbox / words / s_sh free for the next window
             }
-            bar_active(P);  // kbox / kept_* visible, wbox / words / s_sh free for the next window
+            consumed += n_seg;
+            if (!segmented) break;
         }
         if (tid == 0) s_nkeep = n_keep;
         LP_STAMP(4);  // NMS done

@@ -93,6 +93,58 @@ class NmsPlan:
         return self.workspace[: 4 * self.B].view(torch.int32)
 
 
+class NmsPipeline:
+    """Two-stream software pipeline over consecutive batches: K1 (filter, HBM-bound, all SMs it can
+    get) of batch i+1 runs while K2 (sort/NMS/gather, latency-bound, one CTA per image) of batch i
+    is still resolving.  ``depth`` plans alternate so a batch's candidates are not overwritten
+    before its K2 has consumed them.  Results of ``submit`` are valid once ``done[slot]`` fired.
+    """
+
+    def __init__(self, B: int, A: int, max_det: int = 300, device=None, depth: int = 2):
+        self.plans = [NmsPlan(B, A, max_det, device) for _ in range(depth)]
+        self.device = self.plans[0].device
+        with torch.cuda.device(self.device):
+            lo, hi = torch.cuda.Stream.priority_range()
+            self.s_filter = torch.cuda.Stream(self.device, priority=lo)
+            self.s_nms = torch.cuda.Stream(self.device, priority=hi)     # K2 CTAs are dispatched first
+            self.filtered = [torch.cuda.Event() for _ in range(depth)]
+            self.done = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+
+    def start(self):
+        """Order both streams after the caller's current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        self.s_filter.wait_stream(cur)
+        self.s_nms.wait_stream(cur)
+
+    def submit(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, timing=None):
+        """Enqueue one batch; returns (slot, out, counts).  ``timing``: optional pair of CUDA
+        events recorded round the filter launch on its stream."""
+        slot = self.n % len(self.plans)
+        plan = self.plans[slot]
+        with torch.cuda.stream(self.s_filter):
+            if self.n >= len(self.plans):
+                self.s_filter.wait_event(self.done[slot])      # K2 of the batch that used this slot
+            if timing is not None:
+                timing[0].record(self.s_filter)
+            plan.run_filter(pred, conf_thres)
+            if timing is not None:
+                timing[1].record(self.s_filter)
+            self.filtered[slot].record(self.s_filter)
+        with torch.cuda.stream(self.s_nms):
+            self.s_nms.wait_event(self.filtered[slot])
+            plan.run_suppress(pred, iou_thres)
+            self.done[slot].record(self.s_nms)
+        self.n += 1
+        return slot, plan.out, plan.counts
+
+    def finish(self):
+        """Make the caller's stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_filter)
+        cur.wait_stream(self.s_nms)
+
+
 _plans: dict = {}
 
 
