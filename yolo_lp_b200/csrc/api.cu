@@ -207,11 +207,12 @@ LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double
 
 LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream) {
     if (!levels || !out) return LP_E_NULL;
-    if (n_levels <= 0 || n_levels > LP_MAX_LEVELS || B <= 0 || B > 65535) return LP_E_SIZE;
+    if (n_levels <= 0 || n_levels > LP_MAX_LEVELS || B <= 0) return LP_E_SIZE;
     if (!aligned(out, 8)) return LP_E_ALIGN;
     DecodeParams p;
     long long A = 0;
     int tiles = 0;
+    bool bulk = true;
     for (int l = 0; l < n_levels; ++l) {
         const lp_level_t& src = levels[l];
         if (src.h <= 0 || src.w <= 0) return LP_E_SIZE;
@@ -220,6 +221,7 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
         for (int g = 0; g < 8; ++g) {
             if (!src.cls[g]) return LP_E_NULL;
             d.cls[g] = src.cls[g];
+            bulk = bulk && aligned(src.cls[g], 16);
         }
         d.reg = src.reg;
         d.cor = src.cor;
@@ -228,15 +230,19 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
         d.anchor_off = (int)A;
         d.tile_off = tiles;
         d.stride = src.stride;
+        bulk = bulk && aligned(src.reg, 16) && aligned(src.cor, 16) && (d.hw % 4 == 0);
         A += d.hw;
         tiles += (d.hw + DEC_TILE - 1) / DEC_TILE;
-        if (A * (long long)B >= (1ll << 31)) return LP_E_SIZE;
+        if (A * (long long)B >= (1ll << 31) || (long long)tiles * B >= (1ll << 31)) return LP_E_SIZE;
     }
     for (int l = n_levels; l < LP_MAX_LEVELS; ++l) p.lv[l] = p.lv[0];
     p.n_levels = n_levels;
     p.A = (int)A;
+    p.tiles_per_image = tiles;
+    p.n_tiles = tiles * B;
+    p.bulk_in = bulk ? 1 : 0;
     p.out = out;
-    return (int)launch_decode(p, tiles, B, static_cast<cudaStream_t>(stream));
+    return (int)launch_decode(p, num_sms_cached(), static_cast<cudaStream_t>(stream));
 }
 
 LP_API int lp_generate_anchors_f32(const int* h, const int* w, const float* stride, int n_levels, float grid_cell_offset,

@@ -9,87 +9,221 @@
 // Algorithmic traffic: 1156 B read + 1160 B written per anchor (the reference moves the payload
 // roughly three times each way through ~30 launches).
 //
-// A CTA transposes a tile of kTile consecutive positions of one level through shared memory:
-// channel-major coalesced reads (one 128-B line per channel per 32 positions), row-major
-// coalesced 64-bit writes of the finished 1160-B rows.
+// HBM-bound transpose, persistent CTAs (one per SM), software-pipelined over tiles of 32 anchor
+// positions of one level of one image:
+//   in    289 channel rows of 32 positions (128 B each) land channel-major in a shared-memory
+//         stage through 16-byte cp.async copies (LDGSTS.128, no register staging) issued by all
+//         threads; four stages, so the loads of tiles t+1..t+3 fly while tile t is transposed
+//         (111 KB in flight per SM).  (One TMA bulk copy per row was measured first: the TMA unit
+//         serialises such small requests at ~100 cycles each, 4x slower than the LSU path.)
+//         Shapes whose rows are not 16-byte aligned (h*w % 4 != 0) use 4-byte cp.async instead.
+//   xpose lanes run along positions: conflict-free reads of the stage, sigmoid, row-major write
+//         into the finished-row tile (row pitch 290 words -> 2-way conflict, accepted);
+//         box / corner columns are computed by one thread per position.
+//   out   the tile's rows are contiguous in the output: one TMA bulk store (UBLKCP) when the
+//         destination is 16-byte aligned, coalesced 64-bit stores otherwise.
 #include "kernels.cuh"
 
 namespace lp {
 
-constexpr int DEC_THREADS = 256;
+constexpr int DEC_THREADS = 512;
 constexpr int DEC_WARPS = DEC_THREADS / 32;
-constexpr int N_CLS = ROW - 13;   // 277 sigmoid columns
+constexpr int DEC_STAGES = 4;
+constexpr int STAGE_FLOATS = ROW * DEC_TILE;         // [290 columns][32 positions], column 4 unused
+constexpr int OUT_FLOATS = DEC_TILE * ROW;           // [32 positions][290 columns], double-buffered
+constexpr int DEC_SMEM = (DEC_STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4;
 
-__device__ __forceinline__ float sigmoid_f32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
-
-__global__ void __launch_bounds__(DEC_THREADS) decode_kernel(const DecodeParams p) {
-    __shared__ __align__(16) float tile[DEC_TILE * ROW];   // finished rows, packed like the output
-    __shared__ float raw[12][DEC_TILE];                     // ltrb + 8 corner distances
-
-    const int b = blockIdx.y;
-    int l = 0;
-#pragma unroll
-    for (int i = 1; i < LP_MAX_LEVELS; ++i)
-        if (i < p.n_levels && (int)blockIdx.x >= p.lv[i].tile_off) l = i;
-    const DecodeLevel& lv = p.lv[l];
-    const int p0 = ((int)blockIdx.x - lv.tile_off) * DEC_TILE;
-    const int n = min(DEC_TILE, lv.hw - p0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool in = lane < n;
-
-    // class channels: column 13+c of the row; source tensor = group_of(13+c)
-    for (int c = warp; c < N_CLS; c += DEC_WARPS) {
-        const int col = 13 + c;
-        const int g = group_of(col);
-        const int ch = col - group_begin(g);
-        const int width = group_begin(g + 1) - group_begin(g);
-        if (in) {
-            const float x = __ldg(lv.cls[g] + ((size_t)b * width + ch) * lv.hw + p0 + lane);
-            tile[lane * ROW + col] = sigmoid_f32(x);
-        }
-    }
-    for (int c = warp; c < 12; c += DEC_WARPS) {
-        if (in) {
-            const float* src = c < 4 ? lv.reg + ((size_t)b * 4 + c) * lv.hw : lv.cor + ((size_t)b * 8 + (c - 4)) * lv.hw;
-            raw[c][lane] = __ldg(src + p0 + lane);
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < n) {
-        const int t = threadIdx.x;
-        const int pos = p0 + t;
-        const int y = pos / lv.w, x = pos - y * lv.w;
-        const float ax = __fadd_rn((float)x, 0.5f), ay = __fadd_rn((float)y, 0.5f);  // anchor_generator.py:13-14
-        const float s = lv.stride;
-        float* r = tile + t * ROW;
-        // dist2bbox 'xywh' (general.py:31-38) then *= stride (effidehead.py:285)
-        const float x1 = __fsub_rn(ax, raw[0][t]), y1 = __fsub_rn(ay, raw[1][t]);
-        const float x2 = __fadd_rn(ax, raw[2][t]), y2 = __fadd_rn(ay, raw[3][t]);
-        r[0] = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), s);
-        r[1] = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), s);
-        r[2] = __fmul_rn(__fsub_rn(x2, x1), s);
-        r[3] = __fmul_rn(__fsub_rn(y2, y1), s);
-        r[4] = 1.0f;                                             // effidehead.py:290
-        // dist2cor (general.py:51-66) then *= stride (effidehead.py:286)
-        r[5] = __fmul_rn(__fsub_rn(ax, raw[4][t]), s);
-        r[6] = __fmul_rn(__fsub_rn(ay, raw[5][t]), s);
-        r[7] = __fmul_rn(__fsub_rn(ax, raw[6][t]), s);
-        r[8] = __fmul_rn(__fadd_rn(ay, raw[7][t]), s);
-        r[9] = __fmul_rn(__fadd_rn(ax, raw[8][t]), s);
-        r[10] = __fmul_rn(__fadd_rn(ay, raw[9][t]), s);
-        r[11] = __fmul_rn(__fadd_rn(ax, raw[10][t]), s);
-        r[12] = __fmul_rn(__fsub_rn(ay, raw[11][t]), s);
-    }
-    __syncthreads();
-    // n finished rows are contiguous in the output (8-byte aligned: 1160 = 8 * 145)
-    float2* dst = reinterpret_cast<float2*>(p.out + ((size_t)b * p.A + lv.anchor_off + p0) * ROW);
-    const float2* src = reinterpret_cast<const float2*>(tile);
-    for (int i = threadIdx.x; i < n * (ROW / 2); i += DEC_THREADS) dst[i] = src[i];
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) on the SFU (MUFU.EX2 + MUFU.RCP): relative error <= ~2.5e-6
+// for |x| <= 30 (ex2.approx 2^-22.5, the rounded exponent |x| * 6e-8, rcp.approx 1 ulp), inside the
+// 1e-5 bar of the path; larger magnitudes (saturated scores, denormal results) take the libm route.
+__device__ __forceinline__ float sigmoid_f32(float x) {
+    if (fabsf(x) > 30.0f) return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+    return r;
 }
 
-cudaError_t launch_decode(const DecodeParams& p, int n_tiles, int B, cudaStream_t stream) {
-    if (n_tiles <= 0 || B <= 0) return cudaSuccess;
-    decode_kernel<<<dim3(n_tiles, B), DEC_THREADS, 0, stream>>>(p);
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct TileInfo {
+    int b, l, p0, n;
+};
+
+__device__ __forceinline__ TileInfo tile_info(const DecodeParams& p, int tile) {
+    TileInfo t;
+    t.b = tile / p.tiles_per_image;
+    const int r = tile - t.b * p.tiles_per_image;
+    t.l = 0;
+#pragma unroll
+    for (int i = 1; i < LP_MAX_LEVELS; ++i)
+        if (i < p.n_levels && r >= p.lv[i].tile_off) t.l = i;
+    t.p0 = (r - p.lv[t.l].tile_off) * DEC_TILE;
+    t.n = min(DEC_TILE, p.lv[t.l].hw - t.p0);
+    return t;
+}
+
+// source row of output column `col` (col != 4) for image b of level lv
+__device__ __forceinline__ const float* column_src(const DecodeLevel& lv, int b, int col) {
+    if (col < 4) return lv.reg + ((size_t)b * 4 + col) * lv.hw;
+    if (col < 13) return lv.cor + ((size_t)b * 8 + (col - 5)) * lv.hw;
+    const int g = group_of(col);
+    const int width = group_begin(g + 1) - group_begin(g);
+    return lv.cls[g] + ((size_t)b * width + (col - group_begin(g))) * lv.hw;
+}
+
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Which source tensor / channel feeds output column `col` (col != 4): tensor 0..7 = class groups,
+// 8 = reg, 9 = cor.  Fixed per thread and copy slot, so it is decoded once, outside the tile loop.
+__device__ __forceinline__ void column_source(int col, int& tensor, int& ch, int& width) {
+    if (col < 4) { tensor = 8; ch = col; width = 4; }
+    else if (col < 13) { tensor = 9; ch = col - 5; width = 8; }
+    else { tensor = group_of(col); ch = col - group_begin(tensor); width = group_begin(tensor + 1) - group_begin(tensor); }
+}
+__device__ __forceinline__ const float* tensor_base(const DecodeLevel& lv, int tensor) {
+    return tensor == 8 ? lv.reg : tensor == 9 ? lv.cor : lv.cls[tensor];
+}
+
+constexpr int DEC_SLOTS = ((ROW - 1) * (DEC_TILE / 4) + DEC_THREADS - 1) / DEC_THREADS;  // 16-byte copies per thread and tile
+
+// all threads: queue the copies that bring tile `tile` into `stage` (column-major [col][64])
+__device__ __forceinline__ void load_tile(const DecodeParams& p, int tile, float* stage, int tid, const unsigned (&slot)[DEC_SLOTS]) {
+    const TileInfo t = tile_info(p, tile);
+    const DecodeLevel& lv = p.lv[t.l];
+    if (p.bulk_in) {  // rows 16-byte aligned: 16 chunks of 4 positions per row
+#pragma unroll
+        for (int k = 0; k < DEC_SLOTS; ++k) {
+            const unsigned sl = slot[k];  // col | chunk << 9 | tensor << 13 | ch << 17 | width << 23, ~0 = none
+            if (sl == 0xffffffffu) continue;
+            const int col = sl & 511, chunk = (sl >> 9) & 15, tensor = (sl >> 13) & 15, ch = (sl >> 17) & 63, width = sl >> 23;
+            if (chunk * 4 < t.n)
+                cp_async_16(stage + col * DEC_TILE + chunk * 4,
+                            tensor_base(lv, tensor) + ((size_t)t.b * width + ch) * lv.hw + t.p0 + chunk * 4);
+        }
+    } else {
+        for (int ci = tid; ci < (ROW - 1) * DEC_TILE; ci += DEC_THREADS) {
+            const int r = ci / DEC_TILE, q = ci - r * DEC_TILE;
+            const int col = r + (r >= 4);
+            if (q < t.n) cp_async_4(stage + col * DEC_TILE + q, column_src(lv, t.b, col) + t.p0 + q);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodeParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* stage0 = reinterpret_cast<float*>(smem);
+    float* out0 = stage0 + DEC_STAGES * STAGE_FLOATS;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned slot[DEC_SLOTS];
+#pragma unroll
+    for (int k = 0; k < DEC_SLOTS; ++k) {
+        const int ci = tid + k * DEC_THREADS;
+        slot[k] = 0xffffffffu;
+        if (ci < (ROW - 1) * (DEC_TILE / 4)) {
+            const int r = ci / (DEC_TILE / 4), chunk = ci - r * (DEC_TILE / 4);
+            const int col = r + (r >= 4);
+            int tensor, ch, width;
+            column_source(col, tensor, ch, width);
+            slot[k] = (unsigned)col | (unsigned)chunk << 9 | (unsigned)tensor << 13 | (unsigned)ch << 17 | (unsigned)width << 23;
+        }
+    }
+    // prologue: DEC_STAGES-1 tiles in flight
+    const int first = blockIdx.x, step = gridDim.x;
+#pragma unroll
+    for (int k = 0; k < DEC_STAGES - 1; ++k) {
+        if (first + k * step < p.n_tiles) load_tile(p, first + k * step, stage0 + k * STAGE_FLOATS, tid, slot);
+        cp_async_commit();
+    }
+    int it = 0;
+    for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
+        const float* stage = stage0 + (it % DEC_STAGES) * STAGE_FLOATS;
+        float* outt = out0 + (it & 1) * OUT_FLOATS;
+        // the stage of tile it-1 was released by the __syncthreads that ended the previous iteration
+        const int ahead = tile + (DEC_STAGES - 1) * step;
+        if (ahead < p.n_tiles) load_tile(p, ahead, stage0 + ((it + DEC_STAGES - 1) % DEC_STAGES) * STAGE_FLOATS, tid, slot);
+        cp_async_commit();
+        const TileInfo t = tile_info(p, tile);
+        const DecodeLevel& lv = p.lv[t.l];
+        cp_async_wait<DEC_STAGES - 1>();  // this thread's copies of the current tile have landed
+        // the bulk store of tile it-2 must have finished READING this out buffer before it is rewritten
+        if (tid == 0) bulk_wait_read1();
+        __syncthreads();                  // ... and everybody else's copies
+
+        // class columns: lanes along positions (conflict-free stage reads), sigmoid, transposed write
+        if (lane < t.n) {
+            float* orow = outt + lane * ROW;
+#pragma unroll 4
+            for (int col = 13 + warp; col < ROW; col += DEC_WARPS) orow[col] = sigmoid_f32(stage[col * DEC_TILE + lane]);
+        }
+        // box / objectness / corner columns: one thread per position
+        if (warp == DEC_WARPS - 1 && lane < t.n) {
+            const int pos = t.p0 + lane;
+            const int y = pos / lv.w, x = pos - y * lv.w;
+            const float ax = __fadd_rn((float)x, 0.5f), ay = __fadd_rn((float)y, 0.5f);  // anchor_generator.py:13-14
+            const float sd = lv.stride;
+            const float* st = stage + lane;
+            float* r = outt + lane * ROW;
+            // dist2bbox 'xywh' (general.py:31-38) then *= stride (effidehead.py:285)
+            const float x1 = __fsub_rn(ax, st[0 * DEC_TILE]), y1 = __fsub_rn(ay, st[1 * DEC_TILE]);
+            const float x2 = __fadd_rn(ax, st[2 * DEC_TILE]), y2 = __fadd_rn(ay, st[3 * DEC_TILE]);
+            r[0] = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), sd);
+            r[1] = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), sd);
+            r[2] = __fmul_rn(__fsub_rn(x2, x1), sd);
+            r[3] = __fmul_rn(__fsub_rn(y2, y1), sd);
+            r[4] = 1.0f;                                             // effidehead.py:290
+            // dist2cor (general.py:51-66) then *= stride (effidehead.py:286)
+            r[5] = __fmul_rn(__fsub_rn(ax, st[5 * DEC_TILE]), sd);
+            r[6] = __fmul_rn(__fsub_rn(ay, st[6 * DEC_TILE]), sd);
+            r[7] = __fmul_rn(__fsub_rn(ax, st[7 * DEC_TILE]), sd);
+            r[8] = __fmul_rn(__fadd_rn(ay, st[8 * DEC_TILE]), sd);
+            r[9] = __fmul_rn(__fadd_rn(ax, st[9 * DEC_TILE]), sd);
+            r[10] = __fmul_rn(__fadd_rn(ay, st[10 * DEC_TILE]), sd);
+            r[11] = __fmul_rn(__fadd_rn(ax, st[11 * DEC_TILE]), sd);
+            r[12] = __fmul_rn(__fsub_rn(ay, st[12 * DEC_TILE]), sd);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes of outt -> visible to the bulk store
+        __syncthreads();           // also releases this stage for the copies queued next iteration
+
+        // t.n finished rows are contiguous in the output
+        float* dst = p.out + ((size_t)t.b * p.A + lv.anchor_off + t.p0) * ROW;
+        const uint32_t bytes = (uint32_t)t.n * (ROW * 4);
+        if (((reinterpret_cast<uintptr_t>(dst) | bytes) & 15u) == 0) {
+            if (tid == 0) bulk_s2g(dst, outt, bytes);
+        } else {  // 8-byte aligned only (odd row index or odd row count)
+            float2* d2 = reinterpret_cast<float2*>(dst);
+            const float2* s2 = reinterpret_cast<const float2*>(outt);
+            for (int i = tid; i < t.n * (ROW / 2); i += DEC_THREADS) d2[i] = s2[i];
+        }
+        if (tid == 0) bulk_commit();  // one (possibly empty) group per tile keeps wait_group.read 1 exact
+    }
+    cp_async_wait<0>();
+    if (tid == 0) bulk_wait0();
+}
+
+cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream) {
+    if (p.n_tiles <= 0) return cudaSuccess;
+    static_assert(DEC_SMEM <= 227 * 1024, "decode stages exceed shared memory");
+    cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+    if (e != cudaSuccess) return e;
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    decode_kernel<<<grid, DEC_THREADS, DEC_SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 

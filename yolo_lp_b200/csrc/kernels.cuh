@@ -42,7 +42,7 @@ cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
 int nms_sort_smem_keys(unsigned A);
 
 // ---- decode.cu ---------------------------------------------------------------------------------
-constexpr int DEC_TILE = 32;      // anchor positions per CTA
+constexpr int DEC_TILE = 32;      // anchor positions per tile
 struct DecodeLevel {
     const float* cls[8];
     const float* reg;
@@ -56,9 +56,12 @@ struct DecodeParams {
     DecodeLevel lv[LP_MAX_LEVELS];
     int n_levels;
     int A;
+    int tiles_per_image;
+    int n_tiles;      // B * tiles_per_image
+    int bulk_in;      // every channel row is 16-byte aligned: TMA bulk loads
     float* out;
 };
-cudaError_t launch_decode(const DecodeParams& p, int n_tiles, int B, cudaStream_t stream);
+cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream);
 
 // ---- geometry.cu -------------------------------------------------------------------------------
 struct AnchorLevels {

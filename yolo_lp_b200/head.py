@@ -88,6 +88,51 @@ def dist2cor(distance, anchor_points):
     return out
 
 
+class DecodePlan:
+    """Validated, pointer-resolved launch of the decode kernel for a fixed set of level tensors
+    (e.g. the static output buffers of a CUDA-graphed head).  ``run()`` is a single C call."""
+
+    def __init__(self, levels, strides=(8, 16, 32), out: torch.Tensor | None = None):
+        n = len(levels)
+        if not 0 < n <= _abi.MAX_LEVELS or len(strides) != n:
+            raise ValueError("1..4 levels with one stride each")
+        self.arr = (_abi.LpLevel * n)()
+        self.keep = []  # keeps (possibly copied) contiguous inputs alive
+        self.n = n
+        self.B = B = int(levels[0]["reg"].shape[0])
+        self.device = levels[0]["reg"].device
+        A = 0
+        for i, (lv, s) in enumerate(zip(levels, strides)):
+            reg = _cuda_f32(lv["reg"], "reg")
+            _, c, h, w = reg.shape
+            if c != 4:
+                raise ValueError("reg must have 4 channels (use_dfl=False, reg_max=0)")
+            cor = _cuda_f32(lv["cor"], "cor")
+            if tuple(cor.shape) != (B, 8, h, w):
+                raise ValueError(f"cor shape {tuple(cor.shape)}")
+            self.keep += [reg, cor]
+            for g, (name, width) in enumerate(zip(CLS_NAMES, CLS_WIDTH)):
+                t = _cuda_f32(lv[name], name)
+                if tuple(t.shape) != (B, width, h, w):
+                    raise ValueError(f"{name} shape {tuple(t.shape)} != {(B, width, h, w)}")
+                self.keep.append(t)
+                self.arr[i].cls[g] = t.data_ptr()
+            self.arr[i].reg, self.arr[i].cor = reg.data_ptr(), cor.data_ptr()
+            self.arr[i].h, self.arr[i].w, self.arr[i].stride = h, w, float(s)
+            A += h * w
+        self.A = A
+        if out is None:
+            out = torch.empty((B, A, ROW), dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != (B, A, ROW) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous fp32 [B, A, 290] tensor")
+        self.out = out
+
+    def run(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            _abi.call("lp_detect_decode_f32", self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device))
+        return self.out
+
+
 def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None) -> torch.Tensor:
     """Eval tail of ``Detect.forward`` (effidehead.py:247-301, ``use_dfl=False``).
 
@@ -95,39 +140,7 @@ def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None) 
     ``pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w] reg[B,4,h,w] cor[B,8,h,w]``.
     Returns the head tensor ``[B, A, 290]``.
     """
-    n = len(levels)
-    if not 0 < n <= _abi.MAX_LEVELS or len(strides) != n:
-        raise ValueError("1..4 levels with one stride each")
-    arr = (_abi.LpLevel * n)()
-    keep = []  # keep contiguous copies alive until the launch is queued
-    B = int(levels[0]["reg"].shape[0])
-    device = levels[0]["reg"].device
-    A = 0
-    for i, (lv, s) in enumerate(zip(levels, strides)):
-        reg = _cuda_f32(lv["reg"], "reg")
-        _, c, h, w = reg.shape
-        if c != 4:
-            raise ValueError("reg must have 4 channels (use_dfl=False, reg_max=0)")
-        cor = _cuda_f32(lv["cor"], "cor")
-        if tuple(cor.shape) != (B, 8, h, w):
-            raise ValueError(f"cor shape {tuple(cor.shape)}")
-        keep += [reg, cor]
-        for g, (name, width) in enumerate(zip(CLS_NAMES, CLS_WIDTH)):
-            t = _cuda_f32(lv[name], name)
-            if tuple(t.shape) != (B, width, h, w):
-                raise ValueError(f"{name} shape {tuple(t.shape)} != {(B, width, h, w)}")
-            keep.append(t)
-            arr[i].cls[g] = t.data_ptr()
-        arr[i].reg, arr[i].cor = reg.data_ptr(), cor.data_ptr()
-        arr[i].h, arr[i].w, arr[i].stride = h, w, float(s)
-        A += h * w
-    if out is None:
-        out = torch.empty((B, A, ROW), dtype=torch.float32, device=device)
-    elif tuple(out.shape) != (B, A, ROW) or out.dtype != torch.float32 or not out.is_contiguous():
-        raise ValueError("out must be a contiguous fp32 [B, A, 290] tensor")
-    with torch.cuda.device(device):
-        _abi.call("lp_detect_decode_f32", arr, n, B, out.data_ptr(), _stream(device))
-    return out
+    return DecodePlan(levels, strides, out).run()
 
 
 _PRED_ATTRS = tuple(n + "_preds" for n in CLS_NAMES)
