@@ -233,7 +233,9 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
         bulk = bulk && aligned(src.reg, 16) && aligned(src.cor, 16) && (d.hw % 4 == 0);
         A += d.hw;
         tiles += (d.hw + DEC_TILE - 1) / DEC_TILE;
-        if (A * (long long)B >= (1ll << 31) || (long long)tiles * B >= (1ll << 31)) return LP_E_SIZE;
+        // row indices, tile indices and per-tensor element offsets (<= 37 channels) all fit 32 bits
+        if (A * (long long)B >= (1ll << 31) || (long long)tiles * B >= (1ll << 31) ||
+            (long long)B * 37 * d.hw >= (1ll << 31)) return LP_E_SIZE;
     }
     for (int l = n_levels; l < LP_MAX_LEVELS; ++l) p.lv[l] = p.lv[0];
     p.n_levels = n_levels;

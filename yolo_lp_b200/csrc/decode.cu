@@ -36,11 +36,12 @@ constexpr int DEC_SMEM = (DEC_STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4;
 // sigmoid(x) = 1 / (1 + 2^(-x log2 e)) on the SFU (MUFU.EX2 + MUFU.RCP): relative error <= ~2.5e-6
 // for |x| <= 30 (ex2.approx 2^-22.5, the rounded exponent |x| * 6e-8, rcp.approx 1 ulp), inside the
 // 1e-5 bar of the path; larger magnitudes (saturated scores, denormal results) take the libm route.
+__device__ __noinline__ float sigmoid_slow(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 __device__ __forceinline__ float sigmoid_f32(float x) {
-    if (fabsf(x) > 30.0f) return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+    if (fabsf(x) > 30.0f) r = sigmoid_slow(x);
     return r;
 }
 
@@ -57,18 +58,32 @@ struct TileInfo {
     int b, l, p0, n;
 };
 
-__device__ __forceinline__ TileInfo tile_info(const DecodeParams& p, int tile) {
-    TileInfo t;
-    t.b = tile / p.tiles_per_image;
-    const int r = tile - t.b * p.tiles_per_image;
-    t.l = 0;
+// Walks the tiles tile0, tile0 + step, ... of one CTA without dividing: (image, tile-in-image).
+struct TileWalker {
+    int b, r;
+    __device__ __forceinline__ void init(const DecodeParams& p, int tile) {
+        b = tile / p.tiles_per_image;
+        r = tile - b * p.tiles_per_image;
+    }
+    __device__ __forceinline__ void advance(const DecodeParams& p, int step) {
+        r += step;
+        while (r >= p.tiles_per_image) {
+            r -= p.tiles_per_image;
+            ++b;
+        }
+    }
+    __device__ __forceinline__ TileInfo info(const DecodeParams& p) const {
+        TileInfo t;
+        t.b = b;
+        t.l = 0;
 #pragma unroll
-    for (int i = 1; i < LP_MAX_LEVELS; ++i)
-        if (i < p.n_levels && r >= p.lv[i].tile_off) t.l = i;
-    t.p0 = (r - p.lv[t.l].tile_off) * DEC_TILE;
-    t.n = min(DEC_TILE, p.lv[t.l].hw - t.p0);
-    return t;
-}
+        for (int i = 1; i < LP_MAX_LEVELS; ++i)
+            if (i < p.n_levels && r >= p.lv[i].tile_off) t.l = i;
+        t.p0 = (r - p.lv[t.l].tile_off) * DEC_TILE;
+        t.n = min(DEC_TILE, p.lv[t.l].hw - t.p0);
+        return t;
+    }
+};
 
 // source row of output column `col` (col != 4) for image b of level lv
 __device__ __forceinline__ const float* column_src(const DecodeLevel& lv, int b, int col) {
@@ -102,19 +117,21 @@ __device__ __forceinline__ const float* tensor_base(const DecodeLevel& lv, int t
 
 constexpr int DEC_SLOTS = ((ROW - 1) * (DEC_TILE / 4) + DEC_THREADS - 1) / DEC_THREADS;  // 16-byte copies per thread and tile
 
-// all threads: queue the copies that bring tile `tile` into `stage` (column-major [col][64])
-__device__ __forceinline__ void load_tile(const DecodeParams& p, int tile, float* stage, int tid, const unsigned (&slot)[DEC_SLOTS]) {
-    const TileInfo t = tile_info(p, tile);
+// all threads: queue the copies that bring tile `t` into `stage` (column-major [col][32]).
+// Element offsets inside one source tensor fit 32 bits (checked by lp_detect_decode_f32).
+__device__ __forceinline__ void load_tile(const DecodeParams& p, const TileInfo& t, float* stage, int tid,
+                                          const unsigned (&slot)[DEC_SLOTS]) {
     const DecodeLevel& lv = p.lv[t.l];
-    if (p.bulk_in) {  // rows 16-byte aligned: 16 chunks of 4 positions per row
+    if (p.bulk_in) {  // rows 16-byte aligned: 8 chunks of 4 positions per row
+        const unsigned hw = (unsigned)lv.hw, b = (unsigned)t.b, p0 = (unsigned)t.p0;
 #pragma unroll
         for (int k = 0; k < DEC_SLOTS; ++k) {
             const unsigned sl = slot[k];  // col | chunk << 9 | tensor << 13 | ch << 17 | width << 23, ~0 = none
             if (sl == 0xffffffffu) continue;
-            const int col = sl & 511, chunk = (sl >> 9) & 15, tensor = (sl >> 13) & 15, ch = (sl >> 17) & 63, width = sl >> 23;
-            if (chunk * 4 < t.n)
-                cp_async_16(stage + col * DEC_TILE + chunk * 4,
-                            tensor_base(lv, tensor) + ((size_t)t.b * width + ch) * lv.hw + t.p0 + chunk * 4);
+            const unsigned col = sl & 511, chunk4 = ((sl >> 9) & 15) * 4, tensor = (sl >> 13) & 15, ch = (sl >> 17) & 63,
+                           width = sl >> 23;
+            if ((int)chunk4 < t.n)
+                cp_async_16(stage + col * DEC_TILE + chunk4, tensor_base(lv, tensor) + ((b * width + ch) * hw + p0 + chunk4));
         }
     } else {
         for (int ci = tid; ci < (ROW - 1) * DEC_TILE; ci += DEC_THREADS) {
@@ -146,20 +163,26 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
     }
     // prologue: DEC_STAGES-1 tiles in flight
     const int first = blockIdx.x, step = gridDim.x;
+    TileWalker cur, ahead;
+    cur.init(p, first);
+    ahead = cur;
 #pragma unroll
     for (int k = 0; k < DEC_STAGES - 1; ++k) {
-        if (first + k * step < p.n_tiles) load_tile(p, first + k * step, stage0 + k * STAGE_FLOATS, tid, slot);
+        if (first + k * step < p.n_tiles) load_tile(p, ahead.info(p), stage0 + k * STAGE_FLOATS, tid, slot);
         cp_async_commit();
+        ahead.advance(p, step);
     }
     int it = 0;
     for (int tile = first; tile < p.n_tiles; tile += step, ++it) {
         const float* stage = stage0 + (it % DEC_STAGES) * STAGE_FLOATS;
         float* outt = out0 + (it & 1) * OUT_FLOATS;
         // the stage of tile it-1 was released by the __syncthreads that ended the previous iteration
-        const int ahead = tile + (DEC_STAGES - 1) * step;
-        if (ahead < p.n_tiles) load_tile(p, ahead, stage0 + ((it + DEC_STAGES - 1) % DEC_STAGES) * STAGE_FLOATS, tid, slot);
+        if (tile + (DEC_STAGES - 1) * step < p.n_tiles)
+            load_tile(p, ahead.info(p), stage0 + ((it + DEC_STAGES - 1) % DEC_STAGES) * STAGE_FLOATS, tid, slot);
         cp_async_commit();
-        const TileInfo t = tile_info(p, tile);
+        ahead.advance(p, step);
+        const TileInfo t = cur.info(p);
+        cur.advance(p, step);
         const DecodeLevel& lv = p.lv[t.l];
         cp_async_wait<DEC_STAGES - 1>();  // this thread's copies of the current tile have landed
         // the bulk store of tile it-2 must have finished READING this out buffer before it is rewritten
