@@ -116,10 +116,30 @@ LP_API int lp_tune(int key, int value);
  * clock64() stamps at its phase boundaries; NULL switches it off. */
 LP_API int lp_debug_nms_timing(long long* buf);
 
+/* Debug / property tests: the decode kernel's sigmoid evaluated on a flat device array. */
+LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream);
+
 /* Detect.forward eval tail: raw per-level conv outputs -> out[B,A,290],
  * A = sum h*w, levels in order; anchors are computed from the index, never
  * materialised. */
 LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int B, float* out, lp_stream_t stream);
+
+/*
+ * Fused head tail + NMS: raw per-level conv outputs -> detections, without materialising the
+ * [B,A,290] head tensor (effidehead.py:247-301 followed by nms.py:31-130 in one pass over the class
+ * planes).  Same outputs, workspace (lp_nms_workspace_bytes with A = sum h*w) and knobs as
+ * lp_nms_f32; results are bit-identical to lp_detect_decode_f32 followed by lp_nms_f32 on the same
+ * level tensors.  lp_detect_filter_f32 / lp_detect_suppress_f32 are its two stages (KF, K2).
+ */
+LP_API int lp_detect_postprocess_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                     double iou_thres, int max_det, int max_nms, void* workspace,
+                                     size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                                     const float* rescale, int do_round, lp_stream_t stream);
+LP_API int lp_detect_filter_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream);
+LP_API int lp_detect_suppress_f32(const lp_level_t* levels_host, int n_levels, int B, double iou_thres, int max_det,
+                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream);
 
 /* generate_anchors(is_eval=True, mode='af'): anchor_points[A,2], stride_tensor[A]. */
 LP_API int lp_generate_anchors_f32(const int* h_host, const int* w_host, const float* stride_host, int n_levels,

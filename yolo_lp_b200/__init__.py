@@ -21,7 +21,8 @@ __all__ = ["non_max_suppression", "xywh2xyxy", "generate_anchors", "dist2bbox", 
 _LAZY = {
     "non_max_suppression": "nms", "xywh2xyxy": "nms", "NmsPlan": "nms", "non_max_suppression_with_index": "nms",
     "generate_anchors": "head", "dist2bbox": "head", "dist2cor": "head", "detect_decode": "head",
-    "detect_forward_eval": "head", "DetectEval": "head",
+    "detect_forward_eval": "head", "DetectEval": "head", "detect_postprocess": "head", "detect_forward_nms": "head",
+    "DecodePlan": "head", "PostprocessPlan": "head",
     "rescale": "inferer", "rescale_batch": "inferer", "rescale_table": "inferer",
     "install": "patch",
 }

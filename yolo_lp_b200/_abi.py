@@ -39,7 +39,13 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_debug_nms_timing": (c_int, [c_void_p]),
     "lp_tune": (c_int, [c_int, c_int]),
+    "lp_debug_sigmoid_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "lp_detect_decode_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p]),
+    "lp_detect_postprocess_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
+                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+    "lp_detect_suppress_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_generate_anchors_f32": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_float,
                                         c_void_p, c_void_p, c_void_p]),
     "lp_dist2bbox_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),

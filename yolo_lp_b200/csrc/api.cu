@@ -107,10 +107,10 @@ LP_API int lp_tune(int key, int value) {
 
 // shared validation + parameter setup of the two NMS stages
 static int nms_setup(const float* pred, int B, int A, int max_det, void* workspace, size_t workspace_bytes,
-                     FilterParams& f, NmsParams& n) {
-    if (!pred || !workspace) return LP_E_NULL;
+                     FilterParams& f, NmsParams& n, bool need_pred = true) {
+    if ((need_pred && !pred) || !workspace) return LP_E_NULL;
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
-    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN)) return LP_E_ALIGN;
+    if ((need_pred && !aligned(pred, 16)) || !aligned(workspace, WS_ALIGN)) return LP_E_ALIGN;
     const WsLayout w = ws_layout(B, A, max_det);
     if (workspace_bytes < w.total) return LP_E_WORKSPACE;
     char* ws = static_cast<char*>(workspace);
@@ -140,6 +140,8 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.do_round = 0;
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
     n.timing = g_debug_timing;
+    n.from_levels = 0;
+    n.n_levels = 0;
     return LP_OK;
 }
 
@@ -205,11 +207,11 @@ LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double
                                kept_anchor, rescale, do_round, stream);
 }
 
-LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream) {
-    if (!levels || !out) return LP_E_NULL;
+// validates a level table and lays it out for the kernels (anchor / tile offsets per level)
+static int build_levels(const lp_level_t* levels, int n_levels, int B, DecodeLevel (&lv)[LP_MAX_LEVELS], int& A_out,
+                        int& tiles_out, bool& bulk_out) {
+    if (!levels) return LP_E_NULL;
     if (n_levels <= 0 || n_levels > LP_MAX_LEVELS || B <= 0) return LP_E_SIZE;
-    if (!aligned(out, 8)) return LP_E_ALIGN;
-    DecodeParams p;
     long long A = 0;
     int tiles = 0;
     bool bulk = true;
@@ -217,12 +219,14 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
         const lp_level_t& src = levels[l];
         if (src.h <= 0 || src.w <= 0) return LP_E_SIZE;
         if (!src.reg || !src.cor) return LP_E_NULL;
-        DecodeLevel& d = p.lv[l];
+        DecodeLevel& d = lv[l];
         for (int g = 0; g < 8; ++g) {
             if (!src.cls[g]) return LP_E_NULL;
+            if (!aligned(src.cls[g], 4)) return LP_E_ALIGN;
             d.cls[g] = src.cls[g];
             bulk = bulk && aligned(src.cls[g], 16);
         }
+        if (!aligned(src.reg, 4) || !aligned(src.cor, 4)) return LP_E_ALIGN;
         d.reg = src.reg;
         d.cor = src.cor;
         d.w = src.w;
@@ -237,14 +241,113 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
         if (A * (long long)B >= (1ll << 31) || (long long)tiles * B >= (1ll << 31) ||
             (long long)B * 37 * d.hw >= (1ll << 31)) return LP_E_SIZE;
     }
-    for (int l = n_levels; l < LP_MAX_LEVELS; ++l) p.lv[l] = p.lv[0];
+    for (int l = n_levels; l < LP_MAX_LEVELS; ++l) lv[l] = lv[0];
+    A_out = (int)A;
+    tiles_out = tiles;
+    bulk_out = bulk;
+    return LP_OK;
+}
+
+LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream) {
+    if (!out) return LP_E_NULL;
+    if (!aligned(out, 8)) return LP_E_ALIGN;
+    DecodeParams p;
+    int A = 0, tiles = 0;
+    bool bulk = false;
+    const int rc = build_levels(levels, n_levels, B, p.lv, A, tiles, bulk);
+    if (rc != LP_OK) return rc;
     p.n_levels = n_levels;
-    p.A = (int)A;
+    p.A = A;
     p.tiles_per_image = tiles;
     p.n_tiles = tiles * B;
     p.bulk_in = bulk ? 1 : 0;
     p.out = out;
     return (int)launch_decode(p, num_sms_cached(), static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, void* workspace,
+                                size_t workspace_bytes, lp_stream_t stream) {
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
+    LevelsFilterParams k;
+    int A = 0, tiles = 0;
+    bool bulk = false;
+    int rc = build_levels(levels, n_levels, B, k.lv, A, tiles, bulk);
+    if (rc != LP_OK) return rc;
+    FilterParams f;
+    NmsParams n;
+    rc = nms_setup(nullptr, B, A, 0, workspace, (size_t)-1, f, n, false);
+    if (rc != LP_OK) return rc;
+    if (workspace_bytes < ws_layout(B, A, 0).kept_box) return LP_E_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
+    if (e != cudaSuccess) return (int)e;
+    k.n_levels = n_levels;
+    k.tiles_per_image = tiles;
+    k.n_tiles = tiles * B;
+    k.conf = (float)conf_thres;
+    k.keys = f.keys;
+    k.counts = f.counts;
+    k.key_stride = f.key_stride;
+    return (int)launch_levels_filter(k, num_sms_cached(), s);
+}
+
+LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
+                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream) {
+    if (!counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (max_nms <= 0) return LP_E_SIZE;
+    if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    if (!aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    FilterParams f;
+    NmsParams n;
+    DecodeLevel lv[LP_MAX_LEVELS];
+    int A = 0, tiles = 0;
+    bool bulk = false;
+    int rc = build_levels(levels, n_levels, B, lv, A, tiles, bulk);
+    if (rc != LP_OK) return rc;
+    rc = nms_setup(nullptr, B, A, max_det, workspace, workspace_bytes, f, n, false);
+    if (rc != LP_OK) return rc;
+    float iou_floor = (float)iou_thres;
+    if ((double)iou_floor > iou_thres) iou_floor = nextafterf(iou_floor, -INFINITY);
+    n.iou_floor = iou_floor;
+    n.max_nms = max_nms;
+    n.out = out;
+    n.out_counts = counts;
+    n.kept_anchor = kept_anchor;
+    n.rescale = rescale;
+    n.do_round = do_round;
+    n.from_levels = 1;
+    n.n_levels = n_levels;
+    for (int l = 0; l < LP_MAX_LEVELS; ++l) n.lv[l] = lv[l];
+    return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                     int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                     int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                     lp_stream_t stream) {
+    // validate everything before queueing anything
+    if (!workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (max_nms <= 0 || max_det < 0) return LP_E_SIZE;
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    DecodeLevel lv[LP_MAX_LEVELS];
+    int A = 0, tiles = 0;
+    bool bulk = false;
+    int rc = build_levels(levels, n_levels, B, lv, A, tiles, bulk);
+    if (rc != LP_OK) return rc;
+    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
+    if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
+    rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, workspace, workspace_bytes, stream);
+    if (rc != LP_OK) return rc;
+    return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                                  kept_anchor, rescale, do_round, stream);
+}
+
+LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream) {
+    if (!in || !out) return LP_E_NULL;
+    if (n < 0) return LP_E_SIZE;
+    return (int)launch_sigmoid(in, n, out, static_cast<cudaStream_t>(stream));
 }
 
 LP_API int lp_generate_anchors_f32(const int* h, const int* w, const float* stride, int n_levels, float grid_cell_offset,

@@ -75,6 +75,38 @@ __device__ __forceinline__ bool iou_exceeds(const float4& a, float area_a, const
     return ovr > thr_floor;
 }
 
+// ---- head decode arithmetic (effidehead.py:283-286) ------------------------------------------------
+// anchor point of grid cell (x, y): generate_anchors(is_eval=True), anchor_generator.py:13-14
+__device__ __forceinline__ float anchor_coord(int cell) { return __fadd_rn((float)cell, 0.5f); }
+// dist2bbox 'xywh' (general.py:31-38) followed by *= stride (effidehead.py:285): returns cx, cy, w, h
+__device__ __forceinline__ float4 decode_box(float ax, float ay, float l, float t, float r, float b, float stride) {
+    const float x1 = __fsub_rn(ax, l), y1 = __fsub_rn(ay, t), x2 = __fadd_rn(ax, r), y2 = __fadd_rn(ay, b);
+    return make_float4(__fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), stride), __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), stride),
+                       __fmul_rn(__fsub_rn(x2, x1), stride), __fmul_rn(__fsub_rn(y2, y1), stride));
+}
+// dist2cor (general.py:51-66) followed by *= stride (effidehead.py:286): corner k of 8 (TL, BL, BR, TR as x,y pairs)
+__device__ __forceinline__ float decode_corner(int k, float ax, float ay, float d, float stride) {
+    // signs: x: - - + +   y: - + + -
+    const bool is_y = k & 1;
+    const bool plus = is_y ? (k == 3 || k == 5) : (k >= 4);
+    const float a = is_y ? ay : ax;
+    return __fmul_rn(plus ? __fadd_rn(a, d) : __fsub_rn(a, d), stride);
+}
+
+// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) on the SFU (MUFU.EX2 + MUFU.RCP): relative error <= ~2.5e-6
+// for |x| <= 30 (ex2.approx 2^-22.5, the rounded exponent |x| * 6e-8, rcp.approx 1 ulp), inside the
+// 1e-5 bar of the path; larger magnitudes (saturated scores, denormal results) take the libm route.
+// Verified monotone non-decreasing over every finite fp32 input (tools/sigmoid_monotone.py), which
+// is what makes max_j sigmoid(x_j) == sigmoid(max_j x_j) exact in the fused path.
+static __device__ __noinline__ float sigmoid_slow(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+__device__ __forceinline__ float sigmoid_f32(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+    if (fabsf(x) > 30.0f) r = sigmoid_slow(x);
+    return r;
+}
+
 // Inferer.rescale on one coordinate (inferer.py:210-225) + optional caller .round() (:100)
 __device__ __forceinline__ float rescale_coord(float v, float pad, float ratio, float hi, int do_round) {
     v = __fdiv_rn(__fsub_rn(v, pad), ratio);

@@ -33,18 +33,6 @@ constexpr int STAGE_FLOATS = ROW * DEC_TILE;         // [290 columns][32 positio
 constexpr int OUT_FLOATS = DEC_TILE * ROW;           // [32 positions][290 columns], double-buffered
 constexpr int DEC_SMEM = (DEC_STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4;
 
-// sigmoid(x) = 1 / (1 + 2^(-x log2 e)) on the SFU (MUFU.EX2 + MUFU.RCP): relative error <= ~2.5e-6
-// for |x| <= 30 (ex2.approx 2^-22.5, the rounded exponent |x| * 6e-8, rcp.approx 1 ulp), inside the
-// 1e-5 bar of the path; larger magnitudes (saturated scores, denormal results) take the libm route.
-__device__ __noinline__ float sigmoid_slow(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
-__device__ __forceinline__ float sigmoid_f32(float x) {
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
-    if (fabsf(x) > 30.0f) r = sigmoid_slow(x);
-    return r;
-}
-
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
                  "r"(bytes)
@@ -84,15 +72,6 @@ struct TileWalker {
         return t;
     }
 };
-
-// source row of output column `col` (col != 4) for image b of level lv
-__device__ __forceinline__ const float* column_src(const DecodeLevel& lv, int b, int col) {
-    if (col < 4) return lv.reg + ((size_t)b * 4 + col) * lv.hw;
-    if (col < 13) return lv.cor + ((size_t)b * 8 + (col - 5)) * lv.hw;
-    const int g = group_of(col);
-    const int width = group_begin(g + 1) - group_begin(g);
-    return lv.cls[g] + ((size_t)b * width + (col - group_begin(g))) * lv.hw;
-}
 
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -199,27 +178,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
         if (warp == DEC_WARPS - 1 && lane < t.n) {
             const int pos = t.p0 + lane;
             const int y = pos / lv.w, x = pos - y * lv.w;
-            const float ax = __fadd_rn((float)x, 0.5f), ay = __fadd_rn((float)y, 0.5f);  // anchor_generator.py:13-14
+            const float ax = anchor_coord(x), ay = anchor_coord(y);
             const float sd = lv.stride;
             const float* st = stage + lane;
             float* r = outt + lane * ROW;
-            // dist2bbox 'xywh' (general.py:31-38) then *= stride (effidehead.py:285)
-            const float x1 = __fsub_rn(ax, st[0 * DEC_TILE]), y1 = __fsub_rn(ay, st[1 * DEC_TILE]);
-            const float x2 = __fadd_rn(ax, st[2 * DEC_TILE]), y2 = __fadd_rn(ay, st[3 * DEC_TILE]);
-            r[0] = __fmul_rn(__fmul_rn(__fadd_rn(x1, x2), 0.5f), sd);
-            r[1] = __fmul_rn(__fmul_rn(__fadd_rn(y1, y2), 0.5f), sd);
-            r[2] = __fmul_rn(__fsub_rn(x2, x1), sd);
-            r[3] = __fmul_rn(__fsub_rn(y2, y1), sd);
+            const float4 bx = decode_box(ax, ay, st[0 * DEC_TILE], st[1 * DEC_TILE], st[2 * DEC_TILE], st[3 * DEC_TILE], sd);
+            r[0] = bx.x; r[1] = bx.y; r[2] = bx.z; r[3] = bx.w;
             r[4] = 1.0f;                                             // effidehead.py:290
-            // dist2cor (general.py:51-66) then *= stride (effidehead.py:286)
-            r[5] = __fmul_rn(__fsub_rn(ax, st[5 * DEC_TILE]), sd);
-            r[6] = __fmul_rn(__fsub_rn(ay, st[6 * DEC_TILE]), sd);
-            r[7] = __fmul_rn(__fsub_rn(ax, st[7 * DEC_TILE]), sd);
-            r[8] = __fmul_rn(__fadd_rn(ay, st[8 * DEC_TILE]), sd);
-            r[9] = __fmul_rn(__fadd_rn(ax, st[9 * DEC_TILE]), sd);
-            r[10] = __fmul_rn(__fadd_rn(ay, st[10 * DEC_TILE]), sd);
-            r[11] = __fmul_rn(__fadd_rn(ax, st[11 * DEC_TILE]), sd);
-            r[12] = __fmul_rn(__fsub_rn(ay, st[12 * DEC_TILE]), sd);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[5 + k] = decode_corner(k, ax, ay, st[(5 + k) * DEC_TILE], sd);
         }
         fence_proxy_async_smem();  // generic-proxy writes of outt -> visible to the bulk store
         __syncthreads();           // also releases this stage for the copies queued next iteration
@@ -238,6 +205,17 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
     }
     cp_async_wait<0>();
     if (tid == 0) bulk_wait0();
+}
+
+// the device sigmoid on a flat array (debug / property tests: monotonicity, accuracy)
+__global__ void sigmoid_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = sigmoid_f32(in[i]);
+}
+cudaError_t launch_sigmoid(const float* in, long long n, float* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    sigmoid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, n, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream) {

@@ -18,29 +18,6 @@ struct FilterParams {
 };
 cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t stream);
 
-// ---- K2 nms.cu ---------------------------------------------------------------------------------
-struct NmsParams {
-    const float* pred;          // [B, A, 290]
-    unsigned A;
-    unsigned long long* keys;   // [B, key_stride]
-    unsigned key_stride;
-    const int* counts;          // [B] candidates per image (from K1)
-    float iou_floor;            // largest float <= iou_thres
-    int max_det;
-    int max_nms;
-    float4* kept_box;           // [B, max_det] workspace
-    int* kept_anchor_ws;        // [B, max_det] workspace
-    float* out;                 // [B, max_det, 28]
-    int* out_counts;            // [B]
-    int* kept_anchor;           // [B, max_det] or null
-    const float* rescale;       // [B, 5] or null
-    int do_round;
-    int sort_smem_keys;         // capacity of the shared-memory sort buffer (power of two)
-    long long* timing;          // debug only: [B, 8] clock64 stamps per phase, or null
-};
-cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
-int nms_sort_smem_keys(unsigned A);
-
 // ---- decode.cu ---------------------------------------------------------------------------------
 constexpr int DEC_TILE = 32;      // anchor positions per tile
 struct DecodeLevel {
@@ -62,6 +39,58 @@ struct DecodeParams {
     float* out;
 };
 cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_sigmoid(const float* in, long long n, float* out, cudaStream_t stream);
+
+// source plane of output column `col` (col != 4) for image b of level lv
+__device__ __forceinline__ const float* column_src(const DecodeLevel& lv, int b, int col) {
+    if (col < 4) return lv.reg + ((size_t)b * 4 + col) * lv.hw;
+    if (col < 13) return lv.cor + ((size_t)b * 8 + (col - 5)) * lv.hw;
+    const int g = group_of(col);
+    const int width = group_begin(g + 1) - group_begin(g);
+    return lv.cls[g] + ((size_t)b * width + (col - group_begin(g))) * lv.hw;
+}
+
+// ---- KF fused.cu -------------------------------------------------------------------------------
+struct LevelsFilterParams {
+    DecodeLevel lv[LP_MAX_LEVELS];
+    int n_levels;
+    int tiles_per_image;          // tiles of DEC_TILE positions
+    int n_tiles;                  // B * tiles_per_image
+    float conf;
+    unsigned long long* keys;     // [B, key_stride]
+    int* counts;                  // [B], zeroed before launch
+    unsigned key_stride;
+};
+cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream);
+
+
+
+// ---- K2 nms.cu ---------------------------------------------------------------------------------
+struct NmsParams {
+    const float* pred;          // [B, A, 290]
+    unsigned A;
+    unsigned long long* keys;   // [B, key_stride]
+    unsigned key_stride;
+    const int* counts;          // [B] candidates per image (from K1)
+    float iou_floor;            // largest float <= iou_thres
+    int max_det;
+    int max_nms;
+    float4* kept_box;           // [B, max_det] workspace
+    int* kept_anchor_ws;        // [B, max_det] workspace
+    float* out;                 // [B, max_det, 28]
+    int* out_counts;            // [B]
+    int* kept_anchor;           // [B, max_det] or null
+    const float* rescale;       // [B, 5] or null
+    int do_round;
+    int sort_smem_keys;         // capacity of the shared-memory sort buffer (power of two)
+    long long* timing;          // debug only: [B, 16] clock64 stamps per phase, or null
+    // fused path only (from_levels != 0): rows are rebuilt from the raw level tensors, pred is null
+    int from_levels;
+    int n_levels;
+    DecodeLevel lv[LP_MAX_LEVELS];
+};
+cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
+int nms_sort_smem_keys(unsigned A);
 
 // ---- geometry.cu -------------------------------------------------------------------------------
 struct AnchorLevels {

@@ -78,6 +78,9 @@ __device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned nthr
     }
 }
 
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -135,6 +138,35 @@ __device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
     return m;
 }
 
+// anchor index -> (level, position inside the level)
+__device__ __forceinline__ void anchor_to_level(const NmsParams& p, int anchor, int& l, int& pos) {
+    l = 0;
+#pragma unroll
+    for (int i = 1; i < LP_MAX_LEVELS; ++i)
+        if (i < p.n_levels && anchor >= p.lv[i].anchor_off) l = i;
+    pos = anchor - p.lv[l].anchor_off;
+}
+
+// xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- decoded from the raw
+// ltrb planes exactly as the decode kernel does (effidehead.py:283,285)
+template <bool kLevels>
+__device__ __forceinline__ float4 candidate_box(const NmsParams& p, const float* pred, unsigned b, unsigned anchor) {
+    if (!kLevels) {
+        const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
+        const float2 c = __ldg(r), s = __ldg(r + 1);
+        return xywh_to_xyxy(c.x, c.y, s.x, s.y);
+    }
+    int l, pos;
+    anchor_to_level(p, (int)anchor, l, pos);
+    const DecodeLevel& lv = p.lv[l];
+    const float* reg = lv.reg + (size_t)b * 4 * lv.hw + pos;
+    const float d0 = __ldg(reg), d1 = __ldg(reg + lv.hw), d2 = __ldg(reg + 2 * (size_t)lv.hw), d3 = __ldg(reg + 3 * (size_t)lv.hw);
+    const int y = pos / lv.w, x = pos - y * lv.w;
+    const float4 q = decode_box(anchor_coord(x), anchor_coord(y), d0, d1, d2, d3, lv.stride);
+    return xywh_to_xyxy(q.x, q.y, q.z, q.w);
+}
+
+template <bool kLevels>
 __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // sort buffer, later row staging
@@ -151,7 +183,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
 
     const unsigned b = blockIdx.x;
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    const float* pred = p.pred + (size_t)b * p.A * ROW;
+    const float* pred = kLevels ? nullptr : p.pred + (size_t)b * p.A * ROW;
     float4* kept_box = p.kept_box + (size_t)b * p.max_det;
     int* kept_anchor = p.kept_anchor_ws + (size_t)b * p.max_det;
 
@@ -311,9 +343,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                     float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (valid) {
                         anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
-                        const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
-                        const float2 c = __ldg(r), s = __ldg(r + 1);
-                        bx = xywh_to_xyxy(c.x, c.y, s.x, s.y);  // nms.py:79
+                        bx = candidate_box<kLevels>(p, pred, b, anchor);  // nms.py:79
                     }
                     wbox[j] = bx;
                     s_sh[j] = 0;
@@ -442,14 +472,47 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     }
     for (int base = 0; base < n_keep; base += cap_rows) {
         const int nb = min(cap_rows, n_keep - base);
-        for (int i = tid; i < nb * (ROW / 2); i += NMS_THREADS) {
-            const int r = i / (ROW / 2), q = i - r * (ROW / 2);
-            const int k = base + r;
-            const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
-            cp_async_8(srow + r * ROW + 2 * q, pred + (size_t)anchor * ROW + 2 * q);
+        if (!kLevels) {
+            for (int i = tid; i < nb * (ROW / 2); i += NMS_THREADS) {
+                const int r = i / (ROW / 2), q = i - r * (ROW / 2);
+                const int k = base + r;
+                const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+                cp_async_8(srow + r * ROW + 2 * q, pred + (size_t)anchor * ROW + 2 * q);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        } else {
+            // fused path: rebuild the kept rows of the head tensor from the raw level planes, with
+            // the decode kernel's arithmetic (effidehead.py:251-258, 283-290)
+            for (int i = tid; i < nb * ROW; i += NMS_THREADS) {
+                const int r = i / ROW, col = i - r * ROW;
+                const int k = base + r;
+                int l, pos;
+                anchor_to_level(p, k < KEPT_SMEM ? kanchor[k] : kept_anchor[k], l, pos);
+                if (col == 4) srow[i] = 1.0f;
+                else cp_async_4(srow + i, column_src(p.lv[l], (int)b, col) + pos);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int i = tid; i < nb * ROW; i += NMS_THREADS) {
+                const int col = i % ROW;
+                if (col >= 13) srow[i] = sigmoid_f32(srow[i]);
+            }
+            for (int r = tid; r < nb; r += NMS_THREADS) {
+                const int k = base + r;
+                int l, pos;
+                anchor_to_level(p, k < KEPT_SMEM ? kanchor[k] : kept_anchor[k], l, pos);
+                const DecodeLevel& lv = p.lv[l];
+                const int y = pos / lv.w, x = pos - y * lv.w;
+                const float ax = anchor_coord(x), ay = anchor_coord(y);
+                float* row = srow + r * ROW;
+                const float4 q = decode_box(ax, ay, row[0], row[1], row[2], row[3], lv.stride);
+                row[0] = q.x; row[1] = q.y; row[2] = q.z; row[3] = q.w;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) row[5 + c] = decode_corner(c, ax, ay, row[5 + c], lv.stride);
+            }
+            __syncthreads();
         }
-        cp_async_wait_all();
-        __syncthreads();
         if (base == 0) LP_STAMP(6);  // rows staged
         for (int t = tid; t < nb * NGROUP; t += NMS_THREADS) {
             const int r = t >> 3, g = t & 7;
@@ -494,9 +557,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
 cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = (size_t)p.sort_smem_keys * sizeof(unsigned long long);
-    cudaError_t e = cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    nms_kernel<<<B, NMS_THREADS, smem, stream>>>(p);
+    if (p.from_levels) {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        nms_kernel<true><<<B, NMS_THREADS, smem, stream>>>(p);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        nms_kernel<false><<<B, NMS_THREADS, smem, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

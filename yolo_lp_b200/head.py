@@ -88,11 +88,10 @@ def dist2cor(distance, anchor_points):
     return out
 
 
-class DecodePlan:
-    """Validated, pointer-resolved launch of the decode kernel for a fixed set of level tensors
-    (e.g. the static output buffers of a CUDA-graphed head).  ``run()`` is a single C call."""
+class _LevelTable:
+    """Validated ``lp_level_t[]`` for a fixed set of level tensors."""
 
-    def __init__(self, levels, strides=(8, 16, 32), out: torch.Tensor | None = None):
+    def __init__(self, levels, strides):
         n = len(levels)
         if not 0 < n <= _abi.MAX_LEVELS or len(strides) != n:
             raise ValueError("1..4 levels with one stride each")
@@ -121,6 +120,15 @@ class DecodePlan:
             self.arr[i].h, self.arr[i].w, self.arr[i].stride = h, w, float(s)
             A += h * w
         self.A = A
+
+
+class DecodePlan(_LevelTable):
+    """Validated, pointer-resolved launch of the decode kernel for a fixed set of level tensors
+    (e.g. the static output buffers of a CUDA-graphed head).  ``run()`` is a single C call."""
+
+    def __init__(self, levels, strides=(8, 16, 32), out: torch.Tensor | None = None):
+        super().__init__(levels, strides)
+        B, A = self.B, self.A
         if out is None:
             out = torch.empty((B, A, ROW), dtype=torch.float32, device=self.device)
         elif tuple(out.shape) != (B, A, ROW) or out.dtype != torch.float32 or not out.is_contiguous():
@@ -131,6 +139,59 @@ class DecodePlan:
         with torch.cuda.device(self.device):
             _abi.call("lp_detect_decode_f32", self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device))
         return self.out
+
+
+class PostprocessPlan(_LevelTable):
+    """Fused head tail + NMS (``lp_detect_postprocess_f32``): raw level tensors -> detections without
+    materialising ``[B, A, 290]``.  Bit-identical to ``DecodePlan`` followed by ``NmsPlan``."""
+
+    KERNELS_PER_CALL = 2  # lp::levels_filter_kernel, lp::nms_kernel<true>
+
+    def __init__(self, levels, strides=(8, 16, 32), max_det: int = 300, max_nms: int = _abi.MAX_NMS,
+                 want_anchor: bool = False):
+        super().__init__(levels, strides)
+        self.max_det, self.max_nms = int(max_det), int(max_nms)
+        nbytes = _abi.nms_workspace_bytes(self.B, self.A, self.max_det)
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.out = torch.empty((self.B, self.max_det, _abi.OUT), dtype=torch.float32, device=self.device)
+        self.counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
+        self.kept_anchor = (torch.empty((self.B, self.max_det), dtype=torch.int32, device=self.device)
+                            if want_anchor else None)
+
+    def run(self, conf_thres, iou_thres, rescale=None, do_round=False):
+        with torch.cuda.device(self.device):
+            _abi.call("lp_detect_postprocess_f32", self.arr, self.n, self.B, float(conf_thres), float(iou_thres),
+                      self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
+                      self.out.data_ptr(), self.counts.data_ptr(),
+                      self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device))
+        return self.out, self.counts
+
+    def run_filter(self, conf_thres):
+        with torch.cuda.device(self.device):
+            _abi.call("lp_detect_filter_f32", self.arr, self.n, self.B, float(conf_thres), self.workspace.data_ptr(),
+                      self.workspace.numel(), _stream(self.device))
+
+    def run_suppress(self, iou_thres, rescale=None, do_round=False):
+        with torch.cuda.device(self.device):
+            _abi.call("lp_detect_suppress_f32", self.arr, self.n, self.B, float(iou_thres), self.max_det, self.max_nms,
+                      self.workspace.data_ptr(), self.workspace.numel(), self.out.data_ptr(), self.counts.data_ptr(),
+                      self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device))
+        return self.out, self.counts
+
+    def candidate_counts(self) -> torch.Tensor:
+        return self.workspace[: 4 * self.B].view(torch.int32)
+
+
+def detect_postprocess(levels, strides=(8, 16, 32), conf_thres=0.25, iou_thres=0.45, max_det=300):
+    """``non_max_suppression(Detect.forward(x))`` from the raw prediction-conv outputs in two
+    launches (KF + K2); returns the reference's ``list[Tensor[k, 28]]``."""
+    assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
+    assert 0 <= iou_thres <= 1, f'iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided.'
+    plan = PostprocessPlan(levels, strides, max_det)
+    out, counts = plan.run(conf_thres, iou_thres)
+    return [out[b, :k] for b, k in enumerate(counts.cpu().tolist())]
 
 
 def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None) -> torch.Tensor:
@@ -162,6 +223,23 @@ def detect_forward_eval(detect, x):
         lv["cor"] = detect.cor_preds[i](reg_feat)
         levels.append(lv)
     return detect_decode(levels, [float(s) for s in detect.stride])
+
+
+def detect_forward_nms(detect, x, conf_thres=0.25, iou_thres=0.45, max_det=300):
+    """``non_max_suppression(detect(x), ...)`` for a reference-style ``Detect`` module in eval mode:
+    the module's convs, then the fused KF + K2 kernels (no ``[B, A, 290]`` tensor in between)."""
+    if getattr(detect, "use_dfl", False):
+        raise NotImplementedError("use_dfl=True (distillation heads) is outside the LP configs")
+    levels = []
+    for i in range(detect.nl):
+        f = detect.stems[i](x[i])
+        cls_feat = detect.cls_convs[i](f)
+        reg_feat = detect.reg_convs[i](f)
+        lv = {name: getattr(detect, attr)[i](cls_feat) for name, attr in zip(CLS_NAMES, _PRED_ATTRS)}
+        lv["reg"] = detect.reg_preds[i](reg_feat)
+        lv["cor"] = detect.cor_preds[i](reg_feat)
+        levels.append(lv)
+    return detect_postprocess(levels, [float(s) for s in detect.stride], conf_thres, iou_thres, max_det)
 
 
 class DetectEval(torch.nn.Module):
