@@ -127,15 +127,16 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int
 /*
  * Fused head tail + NMS: raw per-level conv outputs -> detections, without materialising the
  * [B,A,290] head tensor (effidehead.py:247-301 followed by nms.py:31-130 in one pass over the class
- * planes).  Same outputs, workspace (lp_nms_workspace_bytes with A = sum h*w) and knobs as
- * lp_nms_f32; results are bit-identical to lp_detect_decode_f32 followed by lp_nms_f32 on the same
+ * planes).  Same outputs and knobs as lp_nms_f32; workspace from lp_detect_workspace_bytes
+ * (A = sum h*w; it additionally holds one finished 28-float row per candidate); results are bit-identical to lp_detect_decode_f32 followed by lp_nms_f32 on the same
  * level tensors.  lp_detect_filter_f32 / lp_detect_suppress_f32 are its two stages (KF, K2).
  */
+LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_bytes);
 LP_API int lp_detect_postprocess_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
                                      double iou_thres, int max_det, int max_nms, void* workspace,
                                      size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                      const float* rescale, int do_round, lp_stream_t stream);
-LP_API int lp_detect_filter_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+LP_API int lp_detect_filter_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres, int max_det,
                                 void* workspace, size_t workspace_bytes, lp_stream_t stream);
 LP_API int lp_detect_suppress_f32(const lp_level_t* levels_host, int n_levels, int B, double iou_thres, int max_det,
                                   int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,

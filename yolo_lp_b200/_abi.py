@@ -43,7 +43,8 @@ SIGNATURES = {
     "lp_detect_decode_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p]),
     "lp_detect_postprocess_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                           c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+    "lp_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
+    "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p]),
     "lp_detect_suppress_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_generate_anchors_f32": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_float,
@@ -95,6 +96,12 @@ def check(fn: str, code: int) -> None:
 
 def call(fn: str, *args) -> None:
     check(fn, getattr(load(), fn)(*args))
+
+
+def detect_workspace_bytes(B: int, A: int, max_det: int) -> int:
+    n = c_size_t(0)
+    call("lp_detect_workspace_bytes", B, A, max_det, ctypes.byref(n))
+    return int(n.value)
 
 
 def nms_workspace_bytes(B: int, A: int, max_det: int) -> int:

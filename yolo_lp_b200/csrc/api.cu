@@ -26,6 +26,7 @@ static unsigned key_stride_for(unsigned A) {
 
 struct WsLayout {
     size_t counts, keys, kept_box, kept_anchor, total;
+    size_t slot_of, rec, total_fused;  // fused path only, after `total`
 };
 static WsLayout ws_layout(int B, int A, int max_det) {
     WsLayout w;
@@ -35,6 +36,9 @@ static WsLayout ws_layout(int B, int A, int max_det) {
     w.kept_box = off;    off = align_up(off + sizeof(float4) * (size_t)B * (size_t)max_det);
     w.kept_anchor = off; off = align_up(off + sizeof(int) * (size_t)B * (size_t)max_det);
     w.total = off;
+    w.slot_of = off;     off = align_up(off + sizeof(unsigned) * (size_t)B * (size_t)A);
+    w.rec = off;         off = align_up(off + sizeof(float) * LP_OUT * (size_t)B * (size_t)A);
+    w.total_fused = off;
     return w;
 }
 
@@ -141,7 +145,8 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
     n.timing = g_debug_timing;
     n.from_levels = 0;
-    n.n_levels = 0;
+    n.rec = reinterpret_cast<const float*>(ws + w.rec);           // only valid in a fused-size workspace
+    n.slot_of = reinterpret_cast<const unsigned*>(ws + w.slot_of);
     return LP_OK;
 }
 
@@ -190,6 +195,13 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
     n.rescale = rescale;
     n.do_round = do_round;
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) {
+    if (!out_bytes) return LP_E_NULL;
+    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
+    *out_bytes = ws_layout(B, A, max_det).total_fused;
+    return LP_OK;
 }
 
 LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
@@ -265,8 +277,9 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     return (int)launch_decode(p, num_sms_cached(), static_cast<cudaStream_t>(stream));
 }
 
-LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, void* workspace,
-                                size_t workspace_bytes, lp_stream_t stream) {
+LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
+    if (max_det < 0) return LP_E_SIZE;
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     LevelsFilterParams k;
     int A = 0, tiles = 0;
@@ -277,10 +290,15 @@ LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, d
     NmsParams n;
     rc = nms_setup(nullptr, B, A, 0, workspace, (size_t)-1, f, n, false);
     if (rc != LP_OK) return rc;
-    if (workspace_bytes < ws_layout(B, A, 0).kept_box) return LP_E_WORKSPACE;
+    // the fused layout depends on max_det through the kept_* arrays that precede slot_of / rec
+    const WsLayout w = ws_layout(B, A, max_det);
+    if (workspace_bytes < w.total_fused) return LP_E_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
     if (e != cudaSuccess) return (int)e;
+    k.A = A;
+    k.rec = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.rec);
+    k.slot_of = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + w.slot_of);
     k.n_levels = n_levels;
     k.tiles_per_image = tiles;
     k.n_tiles = tiles * B;
@@ -307,6 +325,7 @@ LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B,
     if (rc != LP_OK) return rc;
     rc = nms_setup(nullptr, B, A, max_det, workspace, workspace_bytes, f, n, false);
     if (rc != LP_OK) return rc;
+    if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
     float iou_floor = (float)iou_thres;
     if ((double)iou_floor > iou_thres) iou_floor = nextafterf(iou_floor, -INFINITY);
     n.iou_floor = iou_floor;
@@ -317,8 +336,6 @@ LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B,
     n.rescale = rescale;
     n.do_round = do_round;
     n.from_levels = 1;
-    n.n_levels = n_levels;
-    for (int l = 0; l < LP_MAX_LEVELS; ++l) n.lv[l] = lv[l];
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
@@ -337,8 +354,8 @@ LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int
     if (rc != LP_OK) return rc;
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
     if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
-    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
-    rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, workspace, workspace_bytes, stream);
+    if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
+    rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream);
     if (rc != LP_OK) return rc;
     return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
                                   kept_anchor, rescale, do_round, stream);

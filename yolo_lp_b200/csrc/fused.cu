@@ -11,8 +11,15 @@
 // HBM-bound, no shared memory: a warp owns a tile of 32 consecutive positions of one level of one
 // image; lanes run along positions, so every channel read is one fully coalesced 128-byte line and
 // a lane keeps a whole group (<= 37 independent loads) in flight.  Only the 277 class planes are
-// read here (1108 B per anchor); box and corner planes are touched by K2 for candidates only.
+// streamed (1108 B per anchor); box and corner planes are touched for candidates only.
 // Traffic per anchor: 1108 B instead of 1156 + 1160 (decode) + 1160 (K1) = 3476 B.
+//
+// The same pass tracks, per group, the first index of the maximum (torch.max semantics,
+// nms.py:81-88); a surviving lane then decodes its own box and corners (effidehead.py:283-286,
+// nms.py:79) and stores the finished 28-float detection row by slot, so that K2 only has to order,
+// suppress and copy 112-byte records.  The one subtlety -- two different logits rounding to the
+// same sigmoid, where the reference's argmax is the earlier index -- is detected exactly (one more
+// sigmoid per group) and resolved by a rare warp-cooperative pass.
 #include "kernels.cuh"
 
 namespace lp {
@@ -21,18 +28,52 @@ static_assert(DEC_TILE == 32, "a KF tile is one warp wide");
 constexpr int KF_THREADS = 256;
 constexpr int KF_WARPS = KF_THREADS / 32;
 
+// One class group of one anchor (lane).  load: all of the group's logits in flight at once.
+// scan: maximum logit, its FIRST index, and the largest logit that precedes that index (needed to
+// detect ties in sigmoid space, see below).
 template <int WIDTH>
-__device__ __forceinline__ float group_max_logit(const float* __restrict__ base, size_t hw, bool valid) {
-    float v[WIDTH];
+__device__ __forceinline__ void group_load(float (&v)[37], const float* __restrict__ base, size_t hw, bool valid) {
 #pragma unroll
     for (int c = 0; c < WIDTH; ++c) v[c] = valid ? __ldg(base + c * hw) : 0.0f;
-    float m = v[0];
+}
+template <int WIDTH>
+__device__ __forceinline__ void group_scan(const float (&v)[37], float& best, int& arg, float& before) {
+    best = v[0];
+    arg = 0;
+    before = -INFINITY;
 #pragma unroll
-    for (int c = 1; c < WIDTH; ++c) m = fmaxf(m, v[c]);
-    return m;
+    for (int c = 1; c < WIDTH; ++c) {
+        const bool up = v[c] > best;   // strict: the first occurrence of the maximum wins (torch.max)
+        before = up ? best : before;   // best so far == max of everything before index c
+        arg = up ? c : arg;
+        best = up ? v[c] : best;
+    }
 }
 
-__global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const LevelsFilterParams p) {
+// Exact first argmax in sigmoid space for one group of one anchor, warp-cooperative (lanes along the
+// group's columns).  Only reached when two different logits round to the same sigmoid.
+__device__ __noinline__ int group_argmax_exact(const float* plane, size_t hw, int width, int lane) {
+    constexpr int kInvalid = 1 << 20;
+    float best = -INFINITY;
+    int bi = kInvalid;
+    if (lane < width) {
+        best = sigmoid_f32(__ldg(plane + (size_t)lane * hw));
+        bi = lane;
+    }
+    if (lane + 32 < width) {
+        const float v = sigmoid_f32(__ldg(plane + (size_t)(lane + 32) * hw));
+        if (v > best) { best = v; bi = lane + 32; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    return bi;
+}
+
+__global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const LevelsFilterParams p) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * KF_WARPS + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * KF_WARPS;
@@ -47,19 +88,37 @@ __global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const Leve
         const int pos = (r - lv.tile_off) * DEC_TILE + lane;
         const bool valid = pos < lv.hw;
         const size_t hw = (size_t)lv.hw;
-        const size_t off = (size_t)b * hw;  // image offset in units of one channel plane... times width below
+        const size_t off = (size_t)b * hw;  // image offset of a 1-channel plane; times the group width below
 
-        float c[NGROUP];
-        c[0] = group_max_logit<31>(lv.cls[0] + off * 31 + pos, hw, valid);
-        c[1] = group_max_logit<24>(lv.cls[1] + off * 24 + pos, hw, valid);
-        c[2] = group_max_logit<37>(lv.cls[2] + off * 37 + pos, hw, valid);
-        c[3] = group_max_logit<37>(lv.cls[3] + off * 37 + pos, hw, valid);
-        c[4] = group_max_logit<37>(lv.cls[4] + off * 37 + pos, hw, valid);
-        c[5] = group_max_logit<37>(lv.cls[5] + off * 37 + pos, hw, valid);
-        c[6] = group_max_logit<37>(lv.cls[6] + off * 37 + pos, hw, valid);
-        c[7] = group_max_logit<37>(lv.cls[7] + off * 37 + pos, hw, valid);
+        float c[NGROUP], before[NGROUP];
+        int arg[NGROUP];
+        // two register buffers: the loads of group g+1 are in flight while group g is scanned
+        float va[37], vb[37];
+        group_load<31>(va, lv.cls[0] + off * 31 + pos, hw, valid);
+        group_load<24>(vb, lv.cls[1] + off * 24 + pos, hw, valid);
+        group_scan<31>(va, c[0], arg[0], before[0]);
+        group_load<37>(va, lv.cls[2] + off * 37 + pos, hw, valid);
+        group_scan<24>(vb, c[1], arg[1], before[1]);
+        group_load<37>(vb, lv.cls[3] + off * 37 + pos, hw, valid);
+        group_scan<37>(va, c[2], arg[2], before[2]);
+        group_load<37>(va, lv.cls[4] + off * 37 + pos, hw, valid);
+        group_scan<37>(vb, c[3], arg[3], before[3]);
+        group_load<37>(vb, lv.cls[5] + off * 37 + pos, hw, valid);
+        group_scan<37>(va, c[4], arg[4], before[4]);
+        group_load<37>(va, lv.cls[6] + off * 37 + pos, hw, valid);
+        group_scan<37>(vb, c[5], arg[5], before[5]);
+        group_load<37>(vb, lv.cls[7] + off * 37 + pos, hw, valid);
+        group_scan<37>(va, c[6], arg[6], before[6]);
+        group_scan<37>(vb, c[7], arg[7], before[7]);
+        // scores: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
+        // ties: arg is the first index of the maximum LOGIT; the reference takes the first index of
+        // the maximum SIGMOID, which is earlier iff a smaller logit before it rounds to the same value
+        unsigned ties = 0;
 #pragma unroll
-        for (int g = 0; g < NGROUP; ++g) c[g] = __fmul_rn(sigmoid_f32(c[g]), 1.0f);  // cls * obj, obj == 1 (nms.py:76)
+        for (int g = 0; g < NGROUP; ++g) {
+            c[g] = __fmul_rn(sigmoid_f32(c[g]), 1.0f);  // cls * obj, obj == 1 (nms.py:76)
+            if (arg[g] > 0 && sigmoid_f32(before[g]) == c[g]) ties |= 1u << g;
+        }
         float filt, score;
         lp_means(c, filt, score);
 
@@ -69,9 +128,42 @@ __global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const Leve
             int base = 0;
             if (lane == 0) base = atomicAdd(p.counts + b, __popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass)
-                p.keys[(size_t)b * p.key_stride + base + __popc(m & ((1u << lane) - 1u))] =
-                    make_key(score, (unsigned)(lv.anchor_off + pos));
+            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+            // rare: resolve sigmoid-space ties exactly, one survivor and group at a time
+            for (unsigned todo = __ballot_sync(0xffffffffu, pass && ties != 0); todo; todo &= todo - 1) {
+                const int src = __ffs(todo) - 1;
+                const int cpos = __shfl_sync(0xffffffffu, pos, src);
+                const unsigned tg = __shfl_sync(0xffffffffu, ties, src);
+#pragma unroll
+                for (int g = 0; g < NGROUP; ++g) {
+                    if (!((tg >> g) & 1u)) continue;  // warp-uniform
+                    const int width = group_begin(g + 1) - group_begin(g);
+                    const int exact = group_argmax_exact(lv.cls[g] + off * width + cpos, hw, width, lane);
+                    if (lane == src) arg[g] = exact;
+                }
+            }
+            if (pass) {
+                // this lane finishes its own row: box (nms.py:79 on effidehead.py:283,285), corners (:284,286)
+                const unsigned anchor = (unsigned)(lv.anchor_off + pos);
+                p.keys[(size_t)b * p.key_stride + slot] = make_key(score, anchor);
+                p.slot_of[(size_t)b * p.A + anchor] = slot;
+                const float* reg = lv.reg + off * 4 + pos;
+                const float* cor = lv.cor + off * 8 + pos;
+                const int y = pos / lv.w, x = pos - y * lv.w;
+                const float ax = anchor_coord(x), ay = anchor_coord(y);
+                const float4 q = decode_box(ax, ay, __ldg(reg), __ldg(reg + hw), __ldg(reg + 2 * hw), __ldg(reg + 3 * hw), lv.stride);
+                float4* row = reinterpret_cast<float4*>(p.rec + ((size_t)b * p.A + slot) * OUTW);
+                float k[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) k[i] = decode_corner(i, ax, ay, __ldg(cor + i * hw), lv.stride);
+                row[0] = xywh_to_xyxy(q.x, q.y, q.z, q.w);
+                row[1] = make_float4(k[0], k[1], k[2], k[3]);
+                row[2] = make_float4(k[4], k[5], k[6], k[7]);
+                row[3] = make_float4(c[0], c[1], c[2], c[3]);
+                row[4] = make_float4(c[4], c[5], c[6], c[7]);
+                row[5] = make_float4((float)arg[0], (float)arg[1], (float)arg[2], (float)arg[3]);
+                row[6] = make_float4((float)arg[4], (float)arg[5], (float)arg[6], (float)arg[7]);
+            }
         }
         r += n_warps;
         while (r >= p.tiles_per_image) {
@@ -84,7 +176,7 @@ __global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const Leve
 cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream) {
     if (p.n_tiles <= 0) return cudaSuccess;
     int grid = (p.n_tiles + KF_WARPS - 1) / KF_WARPS;
-    const int cap = num_sms * 3;
+    const int cap = num_sms * 2;
     if (grid > cap) grid = cap;
     levels_filter_kernel<<<grid, KF_THREADS, 0, stream>>>(p);
     return cudaGetLastError();

@@ -60,6 +60,9 @@ struct LevelsFilterParams {
     unsigned long long* keys;     // [B, key_stride]
     int* counts;                  // [B], zeroed before launch
     unsigned key_stride;
+    int A;                        // anchors per image
+    float* rec;                   // [B, A, 28] finished detection rows of the candidates, by slot
+    unsigned* slot_of;            // [B, A] slot of a candidate anchor (only candidates are written)
 };
 cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream);
 
@@ -84,10 +87,10 @@ struct NmsParams {
     int do_round;
     int sort_smem_keys;         // capacity of the shared-memory sort buffer (power of two)
     long long* timing;          // debug only: [B, 16] clock64 stamps per phase, or null
-    // fused path only (from_levels != 0): rows are rebuilt from the raw level tensors, pred is null
+    // fused path only (from_levels != 0): KF left the finished rows of every candidate, pred is null
     int from_levels;
-    int n_levels;
-    DecodeLevel lv[LP_MAX_LEVELS];
+    const float* rec;           // [B, A, 28] by slot
+    const unsigned* slot_of;    // [B, A]
 };
 cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream);
 int nms_sort_smem_keys(unsigned A);

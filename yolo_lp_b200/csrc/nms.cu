@@ -138,17 +138,8 @@ __device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
     return m;
 }
 
-// anchor index -> (level, position inside the level)
-__device__ __forceinline__ void anchor_to_level(const NmsParams& p, int anchor, int& l, int& pos) {
-    l = 0;
-#pragma unroll
-    for (int i = 1; i < LP_MAX_LEVELS; ++i)
-        if (i < p.n_levels && anchor >= p.lv[i].anchor_off) l = i;
-    pos = anchor - p.lv[l].anchor_off;
-}
-
-// xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- decoded from the raw
-// ltrb planes exactly as the decode kernel does (effidehead.py:283,285)
+// xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- from the finished
+// row KF stored for it
 template <bool kLevels>
 __device__ __forceinline__ float4 candidate_box(const NmsParams& p, const float* pred, unsigned b, unsigned anchor) {
     if (!kLevels) {
@@ -156,14 +147,8 @@ __device__ __forceinline__ float4 candidate_box(const NmsParams& p, const float*
         const float2 c = __ldg(r), s = __ldg(r + 1);
         return xywh_to_xyxy(c.x, c.y, s.x, s.y);
     }
-    int l, pos;
-    anchor_to_level(p, (int)anchor, l, pos);
-    const DecodeLevel& lv = p.lv[l];
-    const float* reg = lv.reg + (size_t)b * 4 * lv.hw + pos;
-    const float d0 = __ldg(reg), d1 = __ldg(reg + lv.hw), d2 = __ldg(reg + 2 * (size_t)lv.hw), d3 = __ldg(reg + 3 * (size_t)lv.hw);
-    const int y = pos / lv.w, x = pos - y * lv.w;
-    const float4 q = decode_box(anchor_coord(x), anchor_coord(y), d0, d1, d2, d3, lv.stride);
-    return xywh_to_xyxy(q.x, q.y, q.z, q.w);
+    const unsigned slot = __ldg(p.slot_of + (size_t)b * p.A + anchor);
+    return __ldg(reinterpret_cast<const float4*>(p.rec + ((size_t)b * p.A + slot) * OUTW));
 }
 
 template <bool kLevels>
@@ -482,36 +467,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
             cp_async_wait_all();
             __syncthreads();
         } else {
-            // fused path: rebuild the kept rows of the head tensor from the raw level planes, with
-            // the decode kernel's arithmetic (effidehead.py:251-258, 283-290)
-            for (int i = tid; i < nb * ROW; i += NMS_THREADS) {
-                const int r = i / ROW, col = i - r * ROW;
+            // fused path: KF already finished the row of every candidate -- copy the kept ones
+            for (int i = tid; i < nb * OUTW; i += NMS_THREADS) {
+                const int r = i / OUTW, c = i - r * OUTW;
                 const int k = base + r;
-                int l, pos;
-                anchor_to_level(p, k < KEPT_SMEM ? kanchor[k] : kept_anchor[k], l, pos);
-                if (col == 4) srow[i] = 1.0f;
-                else cp_async_4(srow + i, column_src(p.lv[l], (int)b, col) + pos);
+                const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+                const unsigned slot = __ldg(p.slot_of + (size_t)b * p.A + anchor);
+                float val = __ldg(p.rec + ((size_t)b * p.A + slot) * OUTW + c);
+                if (do_rescale && c < 12)
+                    val = (c & 1) ? rescale_coord(val, pad_y, ratio, h0f, p.do_round) : rescale_coord(val, pad_x, ratio, w0f, p.do_round);
+                p.out[((size_t)b * p.max_det + k) * OUTW + c] = val;
+                if (c == 0 && p.kept_anchor != nullptr) p.kept_anchor[(size_t)b * p.max_det + k] = anchor;
             }
-            cp_async_wait_all();
-            __syncthreads();
-            for (int i = tid; i < nb * ROW; i += NMS_THREADS) {
-                const int col = i % ROW;
-                if (col >= 13) srow[i] = sigmoid_f32(srow[i]);
-            }
-            for (int r = tid; r < nb; r += NMS_THREADS) {
-                const int k = base + r;
-                int l, pos;
-                anchor_to_level(p, k < KEPT_SMEM ? kanchor[k] : kept_anchor[k], l, pos);
-                const DecodeLevel& lv = p.lv[l];
-                const int y = pos / lv.w, x = pos - y * lv.w;
-                const float ax = anchor_coord(x), ay = anchor_coord(y);
-                float* row = srow + r * ROW;
-                const float4 q = decode_box(ax, ay, row[0], row[1], row[2], row[3], lv.stride);
-                row[0] = q.x; row[1] = q.y; row[2] = q.z; row[3] = q.w;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) row[5 + c] = decode_corner(c, ax, ay, row[5 + c], lv.stride);
-            }
-            __syncthreads();
+            continue;
         }
         if (base == 0) LP_STAMP(6);  // rows staged
         for (int t = tid; t < nb * NGROUP; t += NMS_THREADS) {

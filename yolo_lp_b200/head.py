@@ -151,7 +151,7 @@ class PostprocessPlan(_LevelTable):
                  want_anchor: bool = False):
         super().__init__(levels, strides)
         self.max_det, self.max_nms = int(max_det), int(max_nms)
-        nbytes = _abi.nms_workspace_bytes(self.B, self.A, self.max_det)
+        nbytes = _abi.detect_workspace_bytes(self.B, self.A, self.max_det)
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.out = torch.empty((self.B, self.max_det, _abi.OUT), dtype=torch.float32, device=self.device)
         self.counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
@@ -169,8 +169,8 @@ class PostprocessPlan(_LevelTable):
 
     def run_filter(self, conf_thres):
         with torch.cuda.device(self.device):
-            _abi.call("lp_detect_filter_f32", self.arr, self.n, self.B, float(conf_thres), self.workspace.data_ptr(),
-                      self.workspace.numel(), _stream(self.device))
+            _abi.call("lp_detect_filter_f32", self.arr, self.n, self.B, float(conf_thres), self.max_det,
+                      self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device))
 
     def run_suppress(self, iou_thres, rescale=None, do_round=False):
         with torch.cuda.device(self.device):
