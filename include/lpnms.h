@@ -116,6 +116,19 @@ LP_API int lp_tune(int key, int value);
  * clock64() stamps at its phase boundaries; NULL switches it off. */
 LP_API int lp_debug_nms_timing(long long* buf);
 
+/*
+ * One pipelined step driven from two streams of the caller (native equivalent of
+ * yolo_lp_b200.nms.NmsPipeline.submit): K1 on filter_stream, K2 on nms_stream, ordered by
+ * filtered_event; workspace_free_event (may be NULL) is the done_event of the step that last used
+ * this workspace; done_event / time_*_event (may be NULL) are recorded after K2 / round K1.
+ * All events are cudaEvent_t handles owned by the caller.
+ */
+LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
+                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                void* done_event, void* time_begin_event, void* time_end_event);
+
 /* Debug / property tests: the decode kernel's sigmoid evaluated on a flat device array. */
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream);
 

@@ -34,6 +34,9 @@ SIGNATURES = {
     "lp_nms_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "lp_nms_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_nms_pipelined_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "lp_nms_filter_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
     "lp_nms_suppress_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

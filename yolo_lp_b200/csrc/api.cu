@@ -197,6 +197,42 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
+LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
+                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                void* done_event, void* time_begin_event, void* time_end_event) {
+    if (!filtered_event) return LP_E_NULL;
+    cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
+    cudaError_t e;
+    if (workspace_free_event) {
+        e = cudaStreamWaitEvent(sf, static_cast<cudaEvent_t>(workspace_free_event), 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (time_begin_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(time_begin_event), sf);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int rc = lp_nms_filter_f32(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream);
+    if (rc != LP_OK) return rc;
+    if (time_end_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaEventRecord(static_cast<cudaEvent_t>(filtered_event), sf);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
+    if (e != cudaSuccess) return (int)e;
+    rc = lp_nms_suppress_f32(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                             rescale, do_round, nms_stream);
+    if (rc != LP_OK) return rc;
+    if (done_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return LP_OK;
+}
+
 LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) {
     if (!out_bytes) return LP_E_NULL;
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;

@@ -125,8 +125,14 @@ __global__ void __launch_bounds__(FILTER_THREADS, 1) filter_kernel(const FilterP
 
 cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t stream) {
     static_assert(FILTER_SMEM <= 227 * 1024, "filter stages exceed shared memory");
-    cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_SMEM);
-    if (e != cudaSuccess) return e;
+    static bool configured[64] = {false};  // per device; idempotent, so a race only repeats the call
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FILTER_SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     unsigned grid = (p.n_tiles + FILTER_WARPS - 1) / FILTER_WARPS;
     if (grid > (unsigned)num_sms) grid = num_sms;
     if (grid == 0) return cudaSuccess;

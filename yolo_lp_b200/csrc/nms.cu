@@ -525,15 +525,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
 cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const size_t smem = (size_t)p.sort_smem_keys * sizeof(unsigned long long);
-    if (p.from_levels) {
+    static bool configured[64] = {false};  // per device; idempotent, so a race only repeats the calls
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        nms_kernel<true><<<B, NMS_THREADS, smem, stream>>>(p);
-    } else {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        nms_kernel<false><<<B, NMS_THREADS, smem, stream>>>(p);
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+    if (p.from_levels) nms_kernel<true><<<B, NMS_THREADS, smem, stream>>>(p);
+    else nms_kernel<false><<<B, NMS_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

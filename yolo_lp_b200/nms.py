@@ -109,6 +109,8 @@ class NmsPipeline:
             self.s_nms = torch.cuda.Stream(self.device, priority=hi)     # K2 CTAs are dispatched first
             self.filtered = [torch.cuda.Event() for _ in range(depth)]
             self.done = [torch.cuda.Event() for _ in range(depth)]
+            for ev in self.filtered + self.done:   # force creation of the cudaEvent_t handles
+                ev.record(self.s_nms)
         self.n = 0
 
     def start(self):
@@ -118,23 +120,21 @@ class NmsPipeline:
         self.s_nms.wait_stream(cur)
 
     def submit(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, timing=None):
-        """Enqueue one batch; returns (slot, out, counts).  ``timing``: optional pair of CUDA
-        events recorded round the filter launch on its stream."""
+        """Enqueue one batch (one native call: lp_nms_pipelined_f32); returns (slot, out, counts).
+        ``timing``: optional pair of CUDA events recorded round the K1 launch on its stream."""
         slot = self.n % len(self.plans)
         plan = self.plans[slot]
-        with torch.cuda.stream(self.s_filter):
-            if self.n >= len(self.plans):
-                self.s_filter.wait_event(self.done[slot])      # K2 of the batch that used this slot
-            if timing is not None:
-                timing[0].record(self.s_filter)
-            plan.run_filter(pred, conf_thres)
-            if timing is not None:
-                timing[1].record(self.s_filter)
-            self.filtered[slot].record(self.s_filter)
-        with torch.cuda.stream(self.s_nms):
-            self.s_nms.wait_event(self.filtered[slot])
-            plan.run_suppress(pred, iou_thres)
-            self.done[slot].record(self.s_nms)
+        if timing is not None:
+            for ev in timing:  # torch creates the cudaEvent_t lazily, on the first record
+                if ev.cuda_event == 0:
+                    ev.record(self.s_filter)
+        _abi.call("lp_nms_pipelined_f32", pred.data_ptr(), plan.B, plan.A, float(conf_thres), float(iou_thres),
+                  plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
+                  plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
+                  self.done[slot].cuda_event if self.n >= len(self.plans) else None,
+                  self.filtered[slot].cuda_event, self.done[slot].cuda_event,
+                  timing[0].cuda_event if timing is not None else None,
+                  timing[1].cuda_event if timing is not None else None)
         self.n += 1
         return slot, plan.out, plan.counts
 
