@@ -13,6 +13,9 @@
 // a lane keeps a whole group (<= 37 independent loads) in flight.  Only the 277 class planes are
 // streamed (1108 B per anchor); box and corner planes are touched for candidates only.
 // Traffic per anchor: 1108 B instead of 1156 + 1160 (decode) + 1160 (K1) = 3476 B.
+// (A variant on the decode kernel's 6-stage cp.async shared-memory ring was measured too: 118 us
+// against 90 us for this register-resident form on the cfg2 shape.  Both stall on HBM efficiency
+// for 128-byte-per-plane segments rather than on latency; 256/512-byte segments are the next step.)
 //
 // The same pass tracks, per group, the first index of the maximum (torch.max semantics,
 // nms.py:81-88); a surviving lane then decodes its own box and corners (effidehead.py:283-286,
