@@ -25,12 +25,11 @@ plan.run(pred, cfg["conf"], cfg["iou"])
 torch.cuda.synchronize()
 _abi.call("lp_debug_nms_timing", None)
 t = buf.cpu()
-names = ["(unused)", "sort", "window0-load", "nms", "gather"]
-t[:, 1] = t[:, 0]
-d = (t[:, 1:6] - t[:, 0:5]).double()
+names = ["order (sort / histogram)", "first segment + window", "nms", "gather"]
+d = torch.stack([t[:, 2] - t[:, 0], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]], 1).double()
 print(f"cfg{cid}: B={B}  candidates/img={plan.candidate_counts().float().mean().item():.0f}  kept/img={plan.counts.float().mean().item():.0f}")
 for i, n in enumerate(names):
-    print(f"  {n:14s} mean {d[:, i].mean():9.0f} clk   max {d[:, i].max():9.0f} clk")
+    print(f"  {n:26s} mean {d[:, i].mean():9.0f} clk   max {d[:, i].max():9.0f} clk")
 g1 = (t[:, 6] - t[:, 4]).double()
 print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk")
 tot = (t[:, 5] - t[:, 0]).double()
