@@ -14,8 +14,7 @@
 // streamed (1108 B per anchor); box and corner planes are touched for candidates only.
 // Traffic per anchor: 1108 B instead of 1156 + 1160 (decode) + 1160 (K1) = 3476 B.
 // (A variant on the decode kernel's 6-stage cp.async shared-memory ring was measured too: 118 us
-// against 90 us for this register-resident form on the cfg2 shape.  Both stall on HBM efficiency
-// for 128-byte-per-plane segments rather than on latency; 256/512-byte segments are the next step.)
+// against 62 us for this register-resident form on the cfg2 shape.)
 //
 // The same pass tracks, per group, the first index of the maximum (torch.max semantics,
 // nms.py:81-88); a surviving lane then decodes its own box and corners (effidehead.py:283-286,
@@ -76,7 +75,7 @@ __device__ __noinline__ int group_argmax_exact(const float* plane, size_t hw, in
     return bi;
 }
 
-__global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const LevelsFilterParams p) {
+__global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const LevelsFilterParams p) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * KF_WARPS + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * KF_WARPS;
@@ -93,35 +92,30 @@ __global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const Leve
         const size_t hw = (size_t)lv.hw;
         const size_t off = (size_t)b * hw;  // image offset of a 1-channel plane; times the group width below
 
-        float c[NGROUP], before[NGROUP];
-        int arg[NGROUP];
-        // two register buffers: the loads of group g+1 are in flight while group g is scanned
-        float va[37], vb[37];
-        group_load<31>(va, lv.cls[0] + off * 31 + pos, hw, valid);
-        group_load<24>(vb, lv.cls[1] + off * 24 + pos, hw, valid);
-        group_scan<31>(va, c[0], arg[0], before[0]);
-        group_load<37>(va, lv.cls[2] + off * 37 + pos, hw, valid);
-        group_scan<24>(vb, c[1], arg[1], before[1]);
-        group_load<37>(vb, lv.cls[3] + off * 37 + pos, hw, valid);
-        group_scan<37>(va, c[2], arg[2], before[2]);
-        group_load<37>(va, lv.cls[4] + off * 37 + pos, hw, valid);
-        group_scan<37>(vb, c[3], arg[3], before[3]);
-        group_load<37>(vb, lv.cls[5] + off * 37 + pos, hw, valid);
-        group_scan<37>(va, c[4], arg[4], before[4]);
-        group_load<37>(va, lv.cls[6] + off * 37 + pos, hw, valid);
-        group_scan<37>(vb, c[5], arg[5], before[5]);
-        group_load<37>(vb, lv.cls[7] + off * 37 + pos, hw, valid);
-        group_scan<37>(va, c[6], arg[6], before[6]);
-        group_scan<37>(vb, c[7], arg[7], before[7]);
-        // scores: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
-        // ties: arg is the first index of the maximum LOGIT; the reference takes the first index of
-        // the maximum SIGMOID, which is earlier iff a smaller logit before it rounds to the same value
+        // Per-group state is folded as soon as the group is scanned (score, 6-bit argmax packed into
+        // `args`, tie bit) so that only one group of loads plus ~12 registers of state stay live:
+        // that keeps three CTAs (24 warps) resident per SM, which this latency-bound kernel needs.
+        //   score: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
+        //   tie:   arg is the first index of the maximum LOGIT; the reference takes the first index of
+        //          the maximum SIGMOID, which is earlier iff a smaller logit before it rounds to the
+        //          same value -- checked exactly with one more sigmoid.
+        float c[NGROUP];
+        unsigned long long args = 0;
         unsigned ties = 0;
-#pragma unroll
-        for (int g = 0; g < NGROUP; ++g) {
-            c[g] = __fmul_rn(sigmoid_f32(c[g]), 1.0f);  // cls * obj, obj == 1 (nms.py:76)
-            if (arg[g] > 0 && sigmoid_f32(before[g]) == c[g]) ties |= 1u << g;
+        float v[37];
+#define LP_GROUP(G, W)                                                                  \
+        {                                                                               \
+            group_load<W>(v, lv.cls[G] + off * W + pos, hw, valid);                     \
+            float best, before;                                                         \
+            int arg;                                                                    \
+            group_scan<W>(v, best, arg, before);                                        \
+            c[G] = __fmul_rn(sigmoid_f32(best), 1.0f); /* cls * obj, obj == 1 (nms.py:76) */ \
+            if (arg > 0 && sigmoid_f32(before) == c[G]) ties |= 1u << G;                \
+            args |= (unsigned long long)arg << (6 * G);                                 \
         }
+        LP_GROUP(0, 31) LP_GROUP(1, 24) LP_GROUP(2, 37) LP_GROUP(3, 37)
+        LP_GROUP(4, 37) LP_GROUP(5, 37) LP_GROUP(6, 37) LP_GROUP(7, 37)
+#undef LP_GROUP
         float filt, score;
         lp_means(c, filt, score);
 
@@ -142,7 +136,7 @@ __global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const Leve
                     if (!((tg >> g) & 1u)) continue;  // warp-uniform
                     const int width = group_begin(g + 1) - group_begin(g);
                     const int exact = group_argmax_exact(lv.cls[g] + off * width + cpos, hw, width, lane);
-                    if (lane == src) arg[g] = exact;
+                    if (lane == src) args = (args & ~(63ull << (6 * g))) | ((unsigned long long)exact << (6 * g));
                 }
             }
             if (pass) {
@@ -164,8 +158,11 @@ __global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const Leve
                 row[2] = make_float4(k[4], k[5], k[6], k[7]);
                 row[3] = make_float4(c[0], c[1], c[2], c[3]);
                 row[4] = make_float4(c[4], c[5], c[6], c[7]);
-                row[5] = make_float4((float)arg[0], (float)arg[1], (float)arg[2], (float)arg[3]);
-                row[6] = make_float4((float)arg[4], (float)arg[5], (float)arg[6], (float)arg[7]);
+                float a[NGROUP];
+#pragma unroll
+                for (int g = 0; g < NGROUP; ++g) a[g] = (float)(unsigned)((args >> (6 * g)) & 63u);
+                row[5] = make_float4(a[0], a[1], a[2], a[3]);
+                row[6] = make_float4(a[4], a[5], a[6], a[7]);
             }
         }
         r += n_warps;
@@ -179,7 +176,7 @@ __global__ void __launch_bounds__(KF_THREADS, 2) levels_filter_kernel(const Leve
 cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream) {
     if (p.n_tiles <= 0) return cudaSuccess;
     int grid = (p.n_tiles + KF_WARPS - 1) / KF_WARPS;
-    const int cap = num_sms * 2;
+    const int cap = num_sms * 3;
     if (grid > cap) grid = cap;
     levels_filter_kernel<<<grid, KF_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
