@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (default: min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the decode-kernel and fused-path side measurements")
     return ap.parse_args()
 
 
@@ -199,6 +200,63 @@ def visible_to_physical(local_index):
     return local_index
 
 
+# --------------------------------------------------------------------------------------------- side rows
+def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
+    """SURVEY 8 rows next to the headline path, on the same shape: the Detect eval-tail decode kernel
+    (raw level tensors -> [B,A,290]) and the fused path (raw level tensors -> detections).  Synthetic
+    level tensors generated on the device; CUDA events; informational (not part of `value`)."""
+    import torch
+    from yolo_lp_b200 import synth
+    from yolo_lp_b200.head import DecodePlan, PostprocessPlan, PostprocessPipeline
+    img = cfg["img"]
+    levels = synth.synth_levels(B, img, img, dev, seed=cfg["seed"])
+    A = cfg["A"]
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(K):
+            fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / K
+
+    dec = DecodePlan(levels, (8, 16, 32))
+    t_dec = timed(dec.run)
+    plans = [PostprocessPlan(levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
+    t_kf = timed(lambda: plans[0].run_filter(conf))
+    t_serial = timed(lambda: plans[0].run(conf, iou))
+    pipe = PostprocessPipeline(plans)
+
+    def burst():
+        pipe.start()
+        for _ in range(K):
+            pipe.submit(conf, iou)
+        pipe.finish()
+    burst()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    burst()
+    b.record()
+    torch.cuda.synchronize(dev)
+    t_pipe = a.elapsed_time(b) / K
+    dec_bytes, kf_bytes = B * A * (289 + 290) * 4, B * A * 277 * 4
+    del dec, plans, pipe, levels
+    torch.cuda.empty_cache()
+    return {
+        "decode_kernel": {"kernel": "lp::decode_kernel", "ms": t_dec, "algorithmic_bytes": dec_bytes,
+                          "achieved_gbs": dec_bytes / t_dec / 1e6, "frac_of_hbm_peak": dec_bytes / t_dec / 1e6 / peak},
+        "fused_path": {"what": "raw level tensors -> detections (lp_detect_postprocess_f32), no [B,A,290] tensor",
+                       "kf_kernel": "lp::levels_filter_kernel", "kf_ms": t_kf, "kf_algorithmic_bytes": kf_bytes,
+                       "kf_achieved_gbs": kf_bytes / t_kf / 1e6, "kf_frac_of_hbm_peak": kf_bytes / t_kf / 1e6 / peak,
+                       "serial_ms_per_step": t_serial, "pipelined_ms_per_step": t_pipe,
+                       "images_per_s_pipelined": B / t_pipe * 1e3, "steps": K}}
+
+
 # --------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch
@@ -333,6 +391,11 @@ def run_ours(args):
            "api": "yolo_lp_b200.non_max_suppression(cpu pinned tensor) -> lp_nms_f32 per 48 MiB chunk"}
     barrier()
 
+    extras = None
+    if not args.no_extras and rank == 0:
+        extras = side_measurements(cfg, B, dev, peak, conf, iou)
+    barrier()
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -341,7 +404,7 @@ def run_ours(args):
                 "p50_batch_latency_ms": statistics.median(step_ms), "p95_batch_latency_ms": sorted(step_ms)[int(0.95 * (Kl - 1))],
                 "serial_stage_ms": {"filter_avg": lat_filter, "nms_avg": lat_nms},
                 "detections_per_image": sum(counts.tolist()) / B, "candidates_per_image": float(cand.sum()) / B,
-                "roofline": roofline, "e2e": e2e, "clocks": clocks.summary(),
+                "roofline": roofline, "e2e": e2e, "clocks": clocks.summary(), "extras": extras,
                 "gpu_launches": K * NmsPlan.KERNELS_PER_CALL}
         if world == 1 and not args.no_cpu_baseline:
             use_all_host_threads()

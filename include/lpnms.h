@@ -155,6 +155,14 @@ LP_API int lp_detect_suppress_f32(const lp_level_t* levels_host, int n_levels, i
                                   int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                   int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream);
 
+/* lp_nms_pipelined_f32 for the fused path: KF on filter_stream, K2 on nms_stream. */
+LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                   double iou_thres, int max_det, int max_nms, void* workspace,
+                                   size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                                   const float* rescale, int do_round, lp_stream_t filter_stream,
+                                   lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                   void* done_event, void* time_begin_event, void* time_end_event);
+
 /* generate_anchors(is_eval=True, mode='af'): anchor_points[A,2], stride_tensor[A]. */
 LP_API int lp_generate_anchors_f32(const int* h_host, const int* w_host, const float* stride_host, int n_levels,
                             float grid_cell_offset, float* anchor_points, float* stride_tensor, lp_stream_t stream);

@@ -446,3 +446,28 @@ def test_device_sigmoid_is_monotone_and_accurate():
             ok = ref > 1e-37
             rel = ((y[::8192].double() - ref).abs() / ref)[ok]
             assert rel.numel() == 0 or float(rel.max()) < 1e-5
+
+
+def test_fused_pipeline_matches_serial_fused_path():
+    from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+    levels_a = synth.synth_levels(4, 320, 320, torch.device(DEV), seed=1)
+    levels_b = synth.synth_levels(4, 320, 320, torch.device(DEV), seed=2)
+    ref = []
+    for lv in (levels_a, levels_b):
+        plan = PostprocessPlan(lv, (8, 16, 32), 300)
+        out, counts = plan.run(0.25, 0.45)
+        ref.append((out.clone(), counts.clone()))
+    pipe = PostprocessPipeline([PostprocessPlan(levels_a, (8, 16, 32), 300), PostprocessPlan(levels_b, (8, 16, 32), 300)])
+    pipe.start()
+    got = []
+    for i in range(6):
+        slot, out, counts = pipe.submit(0.25, 0.45)
+        pipe.done[slot].synchronize()
+        got.append((slot, out.clone(), counts.clone()))
+    pipe.finish()
+    torch.cuda.synchronize()
+    for slot, out, counts in got:
+        assert torch.equal(counts, ref[slot][1])
+        for b, k in enumerate(counts.cpu().tolist()):
+            assert torch.equal(out[b, :k], ref[slot][0][b, :k])
+    assert int(ref[0][1].sum()) > 0

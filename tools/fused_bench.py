@@ -19,21 +19,7 @@ img = int(sys.argv[2]) if len(sys.argv) > 2 else 640
 conf = float(sys.argv[3]) if len(sys.argv) > 3 else 0.25
 iou, max_det = 0.45, 300
 dev = torch.device("cuda:0")
-g = torch.Generator(device=dev).manual_seed(0)
-names, widths = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5"), (31, 24, 37, 37, 37, 37, 37, 37)
-levels = []
-for h, w in synth.level_shapes(img, img):
-    # background logits ~ N(-4.6, 1); ~3.5 % of the anchors carry one confident class per group
-    lv = {}
-    pos = torch.rand((B, 1, h, w), device=dev, generator=g) < 0.035
-    for n, c in zip(names, widths):
-        x = torch.randn((B, c, h, w), device=dev, generator=g) - 4.6
-        hot = torch.randint(c, (B, 1, h, w), device=dev, generator=g)
-        boost = torch.zeros_like(x).scatter_(1, hot, 6.0 + torch.randn((B, 1, h, w), device=dev, generator=g))
-        lv[n] = x + boost * pos
-    lv["reg"] = torch.rand((B, 4, h, w), device=dev, generator=g) * 4 + 1
-    lv["cor"] = torch.rand((B, 8, h, w), device=dev, generator=g) * 4
-    levels.append(lv)
+levels = synth.synth_levels(B, img, img, dev, seed=0)
 A = sum(h * w for h, w in synth.level_shapes(img, img))
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
     if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0

@@ -1,0 +1,43 @@
+#!/usr/bin/env python3
+"""Fused path: KF alone / serial step / two-stream pipelined step vs the KF CTA limit (tuning aid)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from yolo_lp_b200 import _abi, synth
+from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+
+B, img, conf, iou, K = 32, 640, 0.25, 0.45, 100
+dev = torch.device("cuda:0")
+levels = synth.synth_levels(B, img, img, dev, seed=1)
+
+
+def timed(fn, k=K):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(k):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / k * 1e3
+
+
+for ctas in (0, 148, 140, 132, 124, 116, 100):
+    _abi.call("lp_tune", 0, ctas)
+    plans = [PostprocessPlan(levels, (8, 16, 32), 300) for _ in range(2)]
+    t_kf = timed(lambda: plans[0].run_filter(conf))
+    t_s = timed(lambda: plans[0].run(conf, iou))
+    pipe = PostprocessPipeline(plans)
+
+    def burst():
+        pipe.start()
+        for _ in range(K):
+            pipe.submit(conf, iou)
+        pipe.finish()
+    t_p = timed(burst, 3) / K
+    print(f"KF ctas={ctas or 'auto':>4}: KF alone {t_kf:6.1f} us  serial step {t_s:6.1f} us  pipelined step {t_p:6.1f} us ({B / t_p * 1e6:8.0f} img/s)")
+_abi.call("lp_tune", 0, 0)

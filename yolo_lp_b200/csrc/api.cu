@@ -342,7 +342,13 @@ LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, d
     k.keys = f.keys;
     k.counts = f.counts;
     k.key_stride = f.key_stride;
-    return (int)launch_levels_filter(k, num_sms_cached(), s);
+    k.tile_counter = f.tile_counter;
+    // like K1: one persistent CTA per SM, some SMs left free for K2 of the previous batch (KF is
+    // latency-bound and wants more SMs than K1: a sixth is the measured sweet spot)
+    int ctas = num_sms_cached();
+    ctas -= B < ctas / 6 ? B : ctas / 6;
+    if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < num_sms_cached() ? g_filter_cta_limit : num_sms_cached();
+    return (int)launch_levels_filter(k, ctas, s);
 }
 
 LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
@@ -395,6 +401,43 @@ LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int
     if (rc != LP_OK) return rc;
     return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
                                   kept_anchor, rescale, do_round, stream);
+}
+
+LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                   int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                   int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                   lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
+                                   void* filtered_event, void* done_event, void* time_begin_event,
+                                   void* time_end_event) {
+    if (!filtered_event) return LP_E_NULL;
+    cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
+    cudaError_t e;
+    if (workspace_free_event) {
+        e = cudaStreamWaitEvent(sf, static_cast<cudaEvent_t>(workspace_free_event), 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (time_begin_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(time_begin_event), sf);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream);
+    if (rc != LP_OK) return rc;
+    if (time_end_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaEventRecord(static_cast<cudaEvent_t>(filtered_event), sf);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
+    if (e != cudaSuccess) return (int)e;
+    rc = lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                                kept_anchor, rescale, do_round, nms_stream);
+    if (rc != LP_OK) return rc;
+    if (done_event) {
+        e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return LP_OK;
 }
 
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream) {

@@ -27,7 +27,7 @@
 namespace lp {
 
 static_assert(DEC_TILE == 32, "a KF tile is one warp wide");
-constexpr int KF_THREADS = 256;
+constexpr int KF_THREADS = 768;   // one CTA of 24 warps per SM: whole SMs can then be left to K2 (see launch)
 constexpr int KF_WARPS = KF_THREADS / 32;
 
 // One class group of one anchor (lane).  load: all of the group's logits in flight at once.
@@ -75,13 +75,16 @@ __device__ __noinline__ int group_argmax_exact(const float* plane, size_t hw, in
     return bi;
 }
 
-__global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const LevelsFilterParams p) {
+__global__ void __launch_bounds__(KF_THREADS, 1) levels_filter_kernel(const LevelsFilterParams p) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * KF_WARPS + (threadIdx.x >> 5);
     const int n_warps = gridDim.x * KF_WARPS;
-    // (image, tile-in-image) walked without a division per tile
-    int b = gw / p.tiles_per_image, r = gw - b * p.tiles_per_image;
-    for (int tile = gw; tile < p.n_tiles; tile += n_warps) {
+    // tiles: the first one is static (the global warp id), later ones are claimed from a global
+    // counter one claim ahead of use -- keeps every warp busy until the last tile whatever the grid
+    int next = 0x7fffffff;
+    if (lane == 0 && gw < p.n_tiles) next = n_warps + (int)atomicAdd(p.tile_counter, 1u);
+    for (int tile = gw; tile < p.n_tiles;) {
+        const int b = tile / p.tiles_per_image, r = tile - b * p.tiles_per_image;
         int l = 0;
 #pragma unroll
         for (int i = 1; i < LP_MAX_LEVELS; ++i)
@@ -165,19 +168,15 @@ __global__ void __launch_bounds__(KF_THREADS, 3) levels_filter_kernel(const Leve
                 row[6] = make_float4(a[4], a[5], a[6], a[7]);
             }
         }
-        r += n_warps;
-        while (r >= p.tiles_per_image) {
-            r -= p.tiles_per_image;
-            ++b;
-        }
+        tile = __shfl_sync(0xffffffffu, next, 0);
+        if (lane == 0 && tile < p.n_tiles) next = n_warps + (int)atomicAdd(p.tile_counter, 1u);
     }
 }
 
-cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_ctas, cudaStream_t stream) {
     if (p.n_tiles <= 0) return cudaSuccess;
     int grid = (p.n_tiles + KF_WARPS - 1) / KF_WARPS;
-    const int cap = num_sms * 3;
-    if (grid > cap) grid = cap;
+    if (grid > num_ctas) grid = num_ctas;
     levels_filter_kernel<<<grid, KF_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -63,6 +63,7 @@ struct LevelsFilterParams {
     int A;                        // anchors per image
     float* rec;                   // [B, A, 28] finished detection rows of the candidates, by slot
     unsigned* slot_of;            // [B, A] slot of a candidate anchor (only candidates are written)
+    unsigned* tile_counter;       // dynamic tile scheduler, zeroed before launch
 };
 cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_sms, cudaStream_t stream);
 

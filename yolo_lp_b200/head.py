@@ -184,6 +184,53 @@ class PostprocessPlan(_LevelTable):
         return self.workspace[: 4 * self.B].view(torch.int32)
 
 
+class PostprocessPipeline:
+    """Two-stream pipeline of the fused path (native ``lp_detect_pipelined_f32``): KF of batch i+1
+    overlaps K2 of batch i.  ``plans`` are ``PostprocessPlan`` objects (one per in-flight batch, each
+    bound to its own level tensors / workspace); ``submit(k)`` enqueues plan ``k % depth``."""
+
+    def __init__(self, plans):
+        self.plans = list(plans)
+        self.device = self.plans[0].device
+        depth = len(self.plans)
+        with torch.cuda.device(self.device):
+            lo, hi = torch.cuda.Stream.priority_range()
+            self.s_filter = torch.cuda.Stream(self.device, priority=lo)
+            self.s_nms = torch.cuda.Stream(self.device, priority=hi)
+            self.filtered = [torch.cuda.Event() for _ in range(depth)]
+            self.done = [torch.cuda.Event() for _ in range(depth)]
+            for ev in self.filtered + self.done:   # force creation of the cudaEvent_t handles
+                ev.record(self.s_nms)
+        self.n = 0
+
+    def start(self):
+        cur = torch.cuda.current_stream(self.device)
+        self.s_filter.wait_stream(cur)
+        self.s_nms.wait_stream(cur)
+
+    def submit(self, conf_thres, iou_thres, timing=None):
+        slot = self.n % len(self.plans)
+        plan = self.plans[slot]
+        if timing is not None:
+            for ev in timing:
+                if ev.cuda_event == 0:
+                    ev.record(self.s_filter)
+        _abi.call("lp_detect_pipelined_f32", plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
+                  plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
+                  plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
+                  self.done[slot].cuda_event if self.n >= len(self.plans) else None,
+                  self.filtered[slot].cuda_event, self.done[slot].cuda_event,
+                  timing[0].cuda_event if timing is not None else None,
+                  timing[1].cuda_event if timing is not None else None)
+        self.n += 1
+        return slot, plan.out, plan.counts
+
+    def finish(self):
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_filter)
+        cur.wait_stream(self.s_nms)
+
+
 def detect_postprocess(levels, strides=(8, 16, 32), conf_thres=0.25, iou_thres=0.45, max_det=300):
     """``non_max_suppression(Detect.forward(x))`` from the raw prediction-conv outputs in two
     launches (KF + K2); returns the reference's ``list[Tensor[k, 28]]``."""

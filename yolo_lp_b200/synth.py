@@ -75,6 +75,30 @@ def synth_head(B: int, A: int, img: int, n_plates: int, n_pos: int, seed: int,
     return out
 
 
+CLS_NAMES = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5")
+CLS_WIDTH = (31, 24, 37, 37, 37, 37, 37, 37)
+
+
+def synth_levels(B: int, img_h: int, img_w: int, device, seed: int = 0, pos_frac: float = 0.035):
+    """Raw prediction-conv outputs of the three head levels (NCHW fp32, generated ON ``device``) for
+    the decode / fused-path benchmarks: background logits ~N(-4.6, 1) (scores ~0.01) and a fraction
+    ``pos_frac`` of the anchors carrying one confident class per group; ltrb in [1, 5] grid cells."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    levels = []
+    for h, w in level_shapes(img_h, img_w):
+        lv = {}
+        pos = torch.rand((B, 1, h, w), device=device, generator=g) < pos_frac
+        for n, c in zip(CLS_NAMES, CLS_WIDTH):
+            x = torch.randn((B, c, h, w), device=device, generator=g) - 4.6
+            hot = torch.randint(c, (B, 1, h, w), device=device, generator=g)
+            boost = torch.zeros_like(x).scatter_(1, hot, 6.0 + torch.randn((B, 1, h, w), device=device, generator=g))
+            lv[n] = x + boost * pos
+        lv["reg"] = torch.rand((B, 4, h, w), device=device, generator=g) * 4 + 1
+        lv["cor"] = torch.rand((B, 8, h, w), device=device, generator=g) * 4
+        levels.append(lv)
+    return levels
+
+
 def sha256_of(t: torch.Tensor) -> str:
     return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
 
