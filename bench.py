@@ -419,6 +419,25 @@ def run_ours(args):
                 "host_cpus": os.cpu_count(),
                 "sample": f"{passes} passes over {sample.shape[0]} images of {name} ({spent:.1f} s), "
                           f"{CPU_CHUNK}-image calls, torch CPU port of nms.py + torchvision.ops.nms"}
+            # second baseline of SURVEY 8-d: the reference's own GPU route (what tools/infer.py --device 0
+            # does today) -- the same port on CUDA tensors: ~45 ATen launches per image + torchvision's
+            # generic CUDA nms kernel.  Not used for parity (it is not bit-identical to the CPU kernel).
+            try:
+                gsample = sample.to(dev)
+                cpu_pass(gsample, cfg)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                n_img = 0
+                for _ in range(3):
+                    _dt, n = cpu_pass(gsample, cfg)
+                    n_img += n
+                torch.cuda.synchronize(dev)
+                line["reference_cuda_route"] = {
+                    "value": n_img / (time.perf_counter() - t0), "unit": UNIT,
+                    "what": "torch port of the reference on CUDA tensors of the same B200 (ATen kernels + "
+                            "torchvision CUDA nms), input clone included, 8-image calls"}
+            except Exception as exc:  # torchvision CUDA ops missing etc.: report, do not fail the bench
+                line["reference_cuda_route"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
