@@ -471,3 +471,48 @@ def test_fused_pipeline_matches_serial_fused_path():
         for b, k in enumerate(counts.cpu().tolist()):
             assert torch.equal(out[b, :k], ref[slot][0][b, :k])
     assert int(ref[0][1].sum()) > 0
+
+
+# ------------------------------------------------------------------ ordering fall-backs and fuzz
+@pytest.mark.parametrize("A", [16000, 20000])
+def test_degenerate_scores_take_the_full_sort_fallbacks(A):
+    """All scores equal (the true random-init model): the score histogram has one
+    bin, segmentation is refused and the full bitonic sort runs -- in shared memory for 16000
+    candidates, in the global workspace for 20000.  Order is then purely by anchor index."""
+    pred = synth.synth_head(1, A, 1280, 48, 0, seed=12)
+    pred[0, :, 13:] = 0.5
+    g = torch.Generator().manual_seed(4)
+    pred[0, :, 0:2] = torch.rand((A, 2), generator=g) * 1200.0
+    _check_against_oracle(pred, 0.25, 0.45, 300, f"degenerate A={A}")
+
+
+def test_heavy_suppression_walks_many_segments():
+    """Few tight clusters, every anchor a candidate: far fewer than max_det boxes survive, so the
+    greedy walk has to consume every score segment (and every window) of the 8400 candidates."""
+    A = 8400
+    pred = synth.synth_head(2, A, 640, 24, 300, seed=13)
+    g = torch.Generator().manual_seed(5)
+    centres = torch.rand((10, 2), generator=g) * 600.0
+    which = torch.randint(10, (2, A), generator=g)
+    pred[:, :, 0:2] = centres[which] + torch.rand((2, A, 2), generator=g) * 4.0
+    pred[:, :, 2:4] = 60.0
+    got = _check_against_oracle(pred, 0.0, 0.45, 300, "heavy suppression")
+    assert all(r.shape[0] < 100 for r in got)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_nms_fuzz_against_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 4))
+    A = int(rng.choice([7, 64, 100, 333, 777, 1500, 2600, 4100]))
+    n_pos = int(rng.integers(0, max(2, A // 3)))
+    conf = float(rng.choice([0.0, 0.01, 0.05, 0.25, 0.6]))
+    iou = float(rng.choice([0.0, 0.2, 0.45, 0.65, 1.0]))
+    max_det = int(rng.choice([1, 7, 64, 300, 1000]))
+    quant = rng.choice([0, 0, 4, 16])
+    plates = int(rng.choice([1, 3, 12, 40]))
+    pred = synth.synth_head(B, A, 640, plates, n_pos, seed=2000 + seed, quant=int(quant) or None)
+    if seed % 3 == 0:   # objectness != 1 exercises the cls * obj product (nms.py:76)
+        g = torch.Generator().manual_seed(seed)
+        pred[..., 4] = torch.rand(pred.shape[:2], generator=g)
+    _check_against_oracle(pred, conf, iou, max_det, f"fuzz{seed} B{B} A{A} conf{conf} iou{iou} md{max_det} q{quant}")
