@@ -279,6 +279,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout must carry exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout
+        # when NCCL_DEBUG is set) is sent to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, name = workload(args.config)
