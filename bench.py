@@ -131,7 +131,7 @@ def run_reference_arm(args):
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -272,16 +272,13 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:   # launched bare: re-exec under torchrun, one rank per GPU
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000)] + sys.argv
-            sys.exit(subprocess.call(cmd))
+            sys.exit(subprocess.call(cmd, stdout=JSON_OUT.fileno()))
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: yolo_lp_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout must carry exactly one JSON line: NCCL's banner ("NCCL version ...", printed to stdout
-        # when NCCL_DEBUG is set) is sent to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     cfg, name = workload(args.config)
@@ -441,13 +438,24 @@ def run_ours(args):
                             "torchvision CUDA nms), input clone included, 8-image calls"}
             except Exception as exc:  # torchvision CUDA ops missing etc.: report, do not fail the bench
                 line["reference_cuda_route"] = {"unavailable": repr(exc)[:200]}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries print there too (NCCL's
+    "NCCL version ..." banner under torchrun).  Keep a private duplicate of the real stdout for the
+    JSON line and point file descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 if __name__ == "__main__":
     a = parse()
+    JSON_OUT = claim_stdout()
     if a.impl == "reference":
         run_reference_arm(a)
     else:
