@@ -50,7 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``liblpnms.so`` if missing or older than its sources; return its path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("LPNMS_NVCC_EXTRA", "").split()   # e.g. -DLP_NMS_PROFILE for tools/nms_phase_timing.py
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)

@@ -1,6 +1,7 @@
 // extern "C" boundary of liblpnms.so (see include/lpnms.h): argument validation, workspace
-// carving and kernel launches.  No allocation, no synchronisation, no global mutable state
-// (the SM count is cached per device; that cache is idempotent).
+// carving and kernel launches.  No allocation, no synchronisation; the only process-global state
+// is idempotent per-device caches (SM count, kernel attributes) and the two documented
+// debug / tuning hooks (lp_debug_nms_timing, lp_tune).
 #include <math.h>
 
 #include "kernels.cuh"

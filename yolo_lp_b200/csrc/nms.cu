@@ -19,8 +19,8 @@
 //           per candidate, the other threads act as replicas that share the IoU work); a window is
 //           first tested against every box kept so far, then resolved 32 candidates (one chunk) at
 //           a time -- every later candidate collects the bitmask S of chunk members that would
-//           suppress it, the kept members K of the chunk are settled with a ballot fixed point
-//           (exactly the greedy order) and candidates with S & K die.  Serial depth is the number of
+//           suppress it, the chunk's owner warp settles the kept members K in greedy order from those
+//           masks (ballot fixed point) and candidates with S & K die.  Serial depth is the number of
 //           non-empty chunks, IoU work is only done against still-alive members, and everything
 //           stops as soon as max_det rows are kept, which the reference's truncation keep[:max_det]
 //           (nms.py:122-123) makes legal.
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     __shared__ unsigned rank_acc[RANK_SORT_MAX];  // rank-sort partial ranks
     __shared__ unsigned words[32];            // alive bitmask of the window, one word per chunk
     __shared__ unsigned red[32];              // cross-warp reductions
-    __shared__ unsigned s_misc[4];            // [0] segment end bin, [1] segment fill counter
+    __shared__ unsigned s_misc[4];            // [0] segment end bin, [1] segment fill counter, [2] kept mask of the chunk
     __shared__ int s_nkeep;
 
     const unsigned b = blockIdx.x;
@@ -358,6 +358,12 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 if (first_window) { LP_STAMP(3); first_window = false; }  // first window loaded
 
                 int c = -1;
+#ifdef LP_NMS_PROFILE
+                long long pf_hdr = 0, pf_iou = 0, pf_b0 = 0, pf_fix = 0, pf_b2 = 0, pf_n = 0, pf_t = clock64();
+#define LP_PF(acc) do { const long long t1_ = clock64(); acc += t1_ - pf_t; pf_t = t1_; } while (0)
+#else
+#define LP_PF(acc) do { } while (0)
+#endif
                 while (true) {
                     // next chunk that still has alive members; every warp computes it redundantly
                     const unsigned wl = ((int)lane > c && lane < n_chunks) ? words[lane] : 0u;
@@ -366,6 +372,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                     const bool alive = (words[cw] >> lane) & 1u;
                     c = __ffs(nz) - 1;
                     const unsigned A = __shfl_sync(0xffffffffu, wl, c);
+                    LP_PF(pf_hdr);
                     // S: members of chunk c that suppress this thread's candidate if they are kept;
                     // every replica looks at its share of the alive members
                     if ((int)cw >= c && alive) {
@@ -384,6 +391,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                             }
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
+                                if (bit[r] == 0) continue;  // share exhausted (warp-uniform)
                                 const float4 kb = cb[idx[r]];
                                 if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= bit[r];
                             }
@@ -391,45 +399,61 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                         if ((int)cw == c) S &= lower;  // only earlier members of the own chunk count
                         if (S) atomicOr(&s_sh[j], S);
                     }
+                    LP_PF(pf_iou);
                     bar_active(P);
-                    // greedy inside the chunk, computed redundantly by every warp: K_i = A_i and no
-                    // kept earlier member suppresses i.  Iterating K <- F(K) fixes one more leading
-                    // member per round; the unique fixed point is the sequential result.
-                    unsigned K = A;
-                    {
-                        const unsigned sc = s_sh[c * 32 + lane];
+                    LP_PF(pf_b0);
+                    // greedy inside the chunk, settled by the chunk's owner warp: K_i = A_i and no kept
+                    // earlier member suppresses i (lane i holds the suppressor mask of member i).  One
+                    // ballot per round; a shuffle loop over the members was measured 2x slower.
+                    if (owner && (int)cw == c) {
+                        const unsigned sc = s_sh[j];
                         const bool in_a = (A >> lane) & 1u;
-                        while (true) {
-                            const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);
-                            if (K2 == K) break;
+                        unsigned K = A;
+                        while (true) {  // K <- F(K) fixes one more leading member per round; the unique
+                            const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);  // fixed point is
+                            if (K2 == K) break;                                                      // the greedy result
                             K = K2;
                         }
                         const int room = p.max_det - n_keep;
                         if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
-                    }
-                    if (owner) {
-                        if ((int)cw == c) {
-                            if ((K >> lane) & 1u) {
-                                const int k = n_keep + __popc(K & lower);
-                                if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
-                                else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
-                            }
-                            if (lane == 0) words[cw] = 0;  // every member is now kept or suppressed
-                        } else if ((int)cw > c) {
-                            bool still = alive;
-                            if (alive) {
-                                const unsigned S = s_sh[j];
-                                if (S) s_sh[j] = 0;
-                                still = (S & K) == 0;
-                            }
-                            const unsigned word = __ballot_sync(0xffffffffu, still);
-                            if (lane == 0) words[cw] = word;
+                        if ((K >> lane) & 1u) {
+                            const int k = n_keep + __popc(K & lower);
+                            if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
+                            else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
+                        }
+                        if (lane == 0) {
+                            s_misc[2] = K;
+                            words[cw] = 0;  // every member is now kept or suppressed
                         }
                     }
+                    bar_active(P);
+                    const unsigned K = s_misc[2];
+                    if (owner && (int)cw > c) {
+                        bool still = alive;
+                        if (alive) {
+                            const unsigned S = s_sh[j];
+                            if (S) s_sh[j] = 0;
+                            still = (S & K) == 0;
+                        }
+                        const unsigned word = __ballot_sync(0xffffffffu, still);
+                        if (lane == 0) words[cw] = word;
+                    }
                     n_keep += __popc(K);
+                    LP_PF(pf_fix);
                     if (n_keep >= p.max_det) break;
                     bar_active(P);
+                    LP_PF(pf_b2);
+#ifdef LP_NMS_PROFILE
+                    ++pf_n;
+#endif
                 }
+#ifdef LP_NMS_PROFILE
+                if (w0 == 0 && consumed == 0 && p.timing != nullptr && tid == P - 1) {  // last warp: in every step
+                    long long* q = p.timing + (size_t)b * 16 + 8;
+                    q[0] = pf_hdr; q[1] = pf_iou; q[2] = pf_b0; q[3] = pf_fix; q[4] = pf_b2; q[5] = pf_n;
+                }
+#endif
+#undef LP_PF
                 bar_active(P);  // kbox / kept_* visible, wbox / words / s_sh free for the next window
             }
             consumed += n_seg;
