@@ -17,6 +17,8 @@
  *   lp_xywh2xyxy_f32         <- yolov6/utils/nms.py:21-28
  *   lp_rescale_f32           <- yolov6/core/inferer.py:203-228 (+ .round() :100)
  *   lp_rescale_batch_f32     <- same, one launch for a whole [B,max_det,28] batch
+ *   lp_detect_postprocess_f32 <- effidehead.py:247-301 + nms.py:31-130 fused (no head tensor)
+ *   lp_txt_records_f32 / lp_txt_lines_host <- yolov6/core/inferer.py:92-93,103-120 (--save-txt records)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless the
@@ -189,6 +191,19 @@ LP_API int lp_rescale_f32(float* rows, long long k, long long row_stride, float 
 /* Same over det[B,max_det,28] with counts[B] and params[B,5] = pad_x,pad_y,ratio,W0,H0. */
 LP_API int lp_rescale_batch_f32(float* det, const int* counts, int B, int max_det, const float* params,
                          int do_round, lp_stream_t stream);
+
+/*
+ * Caller-side records of Inferer.infer (yolov6/core/inferer.py:92-93,103-120), batched:
+ *   lp_txt_records_f32  det[B,max_det,28] (already rescaled + rounded) + counts[B] + src_wh[B,2]
+ *                       (W0,H0 of the source images) -> records[B,max_det,21] =
+ *                       8 class ids | box_convert(xyxy)/(W0,H0,W0,H0) | 8 corners/(W0,H0)x4 | conf,
+ *                       conf = mean(row[12:19]) (seven of the eight groups, as the reference does);
+ *   lp_txt_lines_host   HOST helper: the --save-txt text of n records ('%g ' * 20, newline-ended),
+ *                       written to buf; LP_E_WORKSPACE if buf is too small.
+ */
+LP_API int lp_txt_records_f32(const float* det, const int* counts, int B, int max_det, const float* src_wh,
+                              float* records, lp_stream_t stream);
+LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, size_t buf_bytes, size_t* written);
 
 #ifdef __cplusplus
 }

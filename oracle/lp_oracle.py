@@ -237,3 +237,32 @@ def rescale(ori_shape, boxes_and_cors, target_shape, do_round=False):
     if do_round:
         v = np.rint(v).astype(f32)
     return v
+
+
+# --------------------------------------------------------------------------- caller-side records
+def txt_records(det, src_shape):
+    """Per-detection ``--save-txt`` record of ``Inferer.infer``, ``yolov6/core/inferer.py:92-93,103-119``
+    (after the rescale + round of ``:100``): ``[8 class ids | xywh / (W0,H0,W0,H0) | 8 corners /
+    (W0,H0)x4 | conf]`` with ``xywh = box_convert(xyxy)`` (``inferer.py:309-316``) and
+    ``conf = mean(row[12:19])`` (seven of the eight groups, ``:113``).  ``det``: [k,28] fp32;
+    ``src_shape``: (H0, W0, ...).  Returns [k,21] fp32."""
+    det = np.asarray(det, f32)
+    h0, w0 = f32(src_shape[0]), f32(src_shape[1])
+    gn = np.array([w0, h0, w0, h0], f32)
+    x1, y1, x2, y2 = det[:, 0], det[:, 1], det[:, 2], det[:, 3]
+    xywh = np.stack([((x1 + x2).astype(f32) / f32(2)).astype(f32), ((y1 + y2).astype(f32) / f32(2)).astype(f32),
+                     (x2 - x1).astype(f32), (y2 - y1).astype(f32)], 1)
+    xywh = (xywh / gn).astype(f32)
+    cor = (det[:, 4:12] / np.tile(gn[:2], 4)).astype(f32)
+    c = det[:, 12:19]
+    s = c[:, 0]
+    for k in range(1, 7):
+        s = (s + c[:, k]).astype(f32)
+    conf = (s / f32(7)).astype(f32)
+    return np.concatenate([det[:, 20:28], xywh, cor, conf[:, None]], 1).astype(f32)
+
+
+def txt_line(record):
+    """The text line of ``inferer.py:118-120``: ``('%g ' * 20).rstrip() % line`` over the first 20 numbers."""
+    vals = tuple(float(v) for v in record[:20])
+    return ('%g ' * len(vals)).rstrip() % vals

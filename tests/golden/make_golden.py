@@ -224,7 +224,38 @@ def make_rescale():
     save("rescale", n=np.array(len(shapes)), **arrays)
 
 
+def make_txt():
+    """--save-txt records: the reference computes them inline in Inferer.infer (inferer.py:92-93,
+    103-120), which needs a model and image files; the expressions below are those lines driven
+    with the reference's own Inferer.rescale / Inferer.box_convert on reference NMS output."""
+    cfg = synth.CONFIGS[1]
+    x = synth.synth_image(cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"], 0)
+    det = ref_nms(x[None].clone(), 0.25, 0.45, max_det=1000)[0]
+    arrays = {}
+    for n, (letterbox, src) in enumerate((((640, 640), (1160, 720, 3)), ((640, 640), (1080, 1920, 3)), ((640, 640), (37, 53, 3)))):
+        d = det.clone()
+        d[:, :12] = RefInferer.rescale(letterbox, d[:, :12], src).round()          # inferer.py:100
+        gn = torch.tensor(src)[[1, 0, 1, 0]]                                        # :92
+        gn_cor = torch.tensor(src)[[1, 0, 1, 0, 1, 0, 1, 0]]                        # :93
+        recs, lines = [], []
+        for output in d:
+            xyxy = output[:4].tolist()
+            corners = output[4:12].tolist()
+            conf = float(output[12:19].mean())                                      # :113
+            xywh = (RefInferer.box_convert(torch.tensor(xyxy).view(1, 4)) / gn).view(-1).tolist()   # :115
+            corners_gn = (torch.tensor(corners) / gn_cor).tolist()                  # :116
+            cls = output[20:].tolist()                                              # :117
+            line = (*cls, *xywh, *corners_gn)                                       # :118
+            lines.append(('%g ' * len(line)).rstrip() % line)                       # :120
+            recs.append(list(line) + [conf])
+        arrays[f"det{n}"] = d.numpy()
+        arrays[f"rec{n}"] = np.array(recs, np.float32)
+        arrays[f"lines{n}"] = np.array(lines)
+        arrays[f"src{n}"] = np.array(src)
+    save("txt_records", n=np.array(3), **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt"]
     for w in which:
         globals()["make_" + w]()

@@ -516,3 +516,41 @@ def test_nms_fuzz_against_oracle(seed):
         g = torch.Generator().manual_seed(seed)
         pred[..., 4] = torch.rand(pred.shape[:2], generator=g)
     _check_against_oracle(pred, conf, iou, max_det, f"fuzz{seed} B{B} A{A} conf{conf} iou{iou} md{max_det} q{quant}")
+
+
+# ------------------------------------------------------------------ caller-side records
+def test_txt_records_kernel_matches_reference_records():
+    from yolo_lp_b200.inferer import txt_records, txt_lines
+    g = golden("txt_records")
+    n = int(g["n"])
+    k = g["det0"].shape[0]
+    det = torch.zeros((n, k + 5, 28))
+    for i in range(n):
+        det[i, :k] = torch.from_numpy(g[f"det{i}"])
+    counts = torch.full((n,), k, dtype=torch.int32)
+    rec = txt_records(det.to(DEV), counts.to(DEV), [g[f"src{i}"].tolist() for i in range(n)]).cpu()
+    for i in range(n):
+        want = g[f"rec{i}"]
+        got = rec[i, :k].numpy()
+        assert np.array_equal(got[:, :20].view(np.uint32), want[:, :20].view(np.uint32)), i
+        np.testing.assert_allclose(got[:, 20], want[:, 20], rtol=1e-6)
+        assert txt_lines(rec[i, :k]) == "".join(l + "\n" for l in g[f"lines{i}"].tolist())
+
+
+def test_inferer_flow_nms_rescale_records_end_to_end():
+    """Inferer.infer's post-model flow (inferer.py:82,100,103-120) in three launches: NMS with the
+    fused rescale + round epilogue, then the record kernel; checked against the oracle chain."""
+    from yolo_lp_b200.inferer import rescale_table, txt_records, txt_lines
+    pred = synth.synth_head(2, 8400, 640, 24, 200, seed=71)
+    ori, src = [(640, 640), (640, 640)], [(1160, 720, 3), (480, 854, 3)]
+    plan = NmsPlan(2, 8400, 1000, torch.device(DEV))
+    out, counts = plan.run(pred.to(DEV), 0.4, 0.45, rescale=rescale_table(ori, src, DEV), do_round=True)
+    rec = txt_records(out, counts, src).cpu()
+    want = lp_oracle.non_max_suppression(pred.numpy(), 0.4, 0.45, max_det=1000)
+    for b, k in enumerate(counts.cpu().tolist()):
+        rows = want[b].copy()
+        assert k == rows.shape[0] > 0
+        rows[:, :12] = lp_oracle.rescale(ori[b], rows[:, :12], src[b], do_round=True)
+        wrec = lp_oracle.txt_records(rows, src[b])
+        assert np.array_equal(rec[b, :k, :20].numpy().view(np.uint32), wrec[:, :20].view(np.uint32))
+        assert txt_lines(rec[b, :k]) == "".join(lp_oracle.txt_line(r) + "\n" for r in wrec)

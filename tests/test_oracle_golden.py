@@ -93,3 +93,22 @@ def test_rescale_oracle():
         assert np.array_equal(got, g[f"round{n}"]), n
         tp = torch_port.rescale((hi, wi), torch.from_numpy(g[f"in{n}"].copy()), (h0, w0, 3))
         assert np.array_equal(tp.numpy().view(np.uint32), g[f"out{n}"].view(np.uint32)), n
+
+
+def test_txt_records_oracle_and_native_formatter():
+    """--save-txt records (inferer.py:92-93,103-120): numeric record bit-exact (conf: torch.mean vs a
+    sequential sum, 1 ulp), text lines identical -- both for the oracle's '%g' and for the
+    library's native host formatter (lp_txt_lines_host, no GPU involved)."""
+    from yolo_lp_b200 import build
+    from yolo_lp_b200.inferer import txt_lines
+    build.build()
+    g = golden("txt_records")
+    for n in range(int(g["n"])):
+        rec = lp_oracle.txt_records(g[f"det{n}"], g[f"src{n}"].tolist())
+        want = g[f"rec{n}"]
+        assert np.array_equal(rec[:, :20].view(np.uint32), want[:, :20].view(np.uint32))
+        np.testing.assert_allclose(rec[:, 20], want[:, 20], rtol=1e-6)
+        lines = g[f"lines{n}"].tolist()
+        assert [lp_oracle.txt_line(r) for r in rec] == lines
+        assert txt_lines(torch.from_numpy(want)) == "".join(l + "\n" for l in lines)
+    assert txt_lines(torch.zeros((0, 21))) == ""

@@ -24,6 +24,7 @@ _LAZY = {
     "detect_forward_eval": "head", "DetectEval": "head", "detect_postprocess": "head", "detect_forward_nms": "head",
     "DecodePlan": "head", "PostprocessPlan": "head",
     "rescale": "inferer", "rescale_batch": "inferer", "rescale_table": "inferer",
+    "txt_records": "inferer", "txt_lines": "inferer",
     "install": "patch",
 }
 

@@ -60,6 +60,8 @@ SIGNATURES = {
     "lp_xywh2xyxy_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_void_p]),
     "lp_rescale_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_float, c_float, c_float, c_float, c_float,
                                c_int, c_void_p]),
+    "lp_txt_records_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "lp_txt_lines_host": (c_int, [c_void_p, c_longlong, ctypes.c_char_p, c_size_t, POINTER(c_size_t)]),
     "lp_rescale_batch_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 

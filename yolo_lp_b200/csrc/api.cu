@@ -3,6 +3,7 @@
 // is idempotent per-device caches (SM count, kernel attributes) and the two documented
 // debug / tuning hooks (lp_debug_nms_timing, lp_tune).
 #include <math.h>
+#include <stdio.h>
 
 #include "kernels.cuh"
 
@@ -503,6 +504,30 @@ LP_API int lp_rescale_batch_f32(float* det, const int* counts, int B, int max_de
     if (!det || !counts || !params) return LP_E_NULL;
     if (B <= 0 || B > 65535 || max_det < 0) return LP_E_SIZE;
     return (int)launch_rescale_batch(det, counts, B, max_det, params, do_round, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_txt_records_f32(const float* det, const int* counts, int B, int max_det, const float* src_wh,
+                              float* records, lp_stream_t stream) {
+    if (!det || !counts || !src_wh || !records) return LP_E_NULL;
+    if (B <= 0 || B > 65535 || max_det < 0) return LP_E_SIZE;
+    return (int)launch_txt_records(det, counts, B, max_det, src_wh, records, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, size_t buf_bytes, size_t* written) {
+    if ((!records_host && n > 0) || !buf || !written) return LP_E_NULL;
+    if (n < 0) return LP_E_SIZE;
+    size_t off = 0;
+    for (long long r = 0; r < n; ++r) {
+        const float* v = records_host + r * 21;
+        for (int i = 0; i < 20; ++i) {  // ('%g ' * 20).rstrip() % line, inferer.py:120
+            const int m = snprintf(buf + off, off < buf_bytes ? buf_bytes - off : 0, i == 19 ? "%g\n" : "%g ", (double)v[i]);
+            if (m < 0) return LP_E_ARG;
+            off += (size_t)m;
+            if (off >= buf_bytes) return LP_E_WORKSPACE;
+        }
+    }
+    *written = off;
+    return LP_OK;
 }
 
 }  // extern "C"

@@ -78,6 +78,31 @@ __global__ void rescale_batch_kernel(float* det, const int* __restrict__ counts,
     *v = (c & 1) ? rescale_coord(*v, q[1], q[2], q[4], do_round) : rescale_coord(*v, q[0], q[2], q[3], do_round);
 }
 
+// --save-txt record of Inferer.infer (inferer.py:92-93,103-119), one thread per detection:
+// [8 class ids | box_convert(xyxy) / (W0,H0,W0,H0) | 8 corners / (W0,H0)x4 | mean(row[12:19])]
+__global__ void txt_records_kernel(const float* __restrict__ det, const int* __restrict__ counts, int max_det,
+                                   const float* __restrict__ src_wh, float* __restrict__ rec) {
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(counts[b], max_det)) return;
+    const float* r = det + ((size_t)b * max_det + k) * OUTW;
+    float* o = rec + ((size_t)b * max_det + k) * 21;
+    const float w0 = src_wh[2 * b], h0 = src_wh[2 * b + 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = r[20 + i];                               // inferer.py:117
+    // box_convert (inferer.py:309-316) then / gn (:115); true fp32 divisions
+    o[8] = __fdiv_rn(__fmul_rn(__fadd_rn(r[0], r[2]), 0.5f), w0);
+    o[9] = __fdiv_rn(__fmul_rn(__fadd_rn(r[1], r[3]), 0.5f), h0);
+    o[10] = __fdiv_rn(__fsub_rn(r[2], r[0]), w0);
+    o[11] = __fdiv_rn(__fsub_rn(r[3], r[1]), h0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[12 + i] = __fdiv_rn(r[4 + i], (i & 1) ? h0 : w0);   // :116
+    float s = r[12];
+#pragma unroll
+    for (int i = 13; i < 19; ++i) s = __fadd_rn(s, r[i]);                       // :113, seven of the eight groups
+    o[20] = __fdiv_rn(s, 7.0f);
+}
+
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 cudaError_t launch_anchors(const AnchorLevels& lv, float* points, float* strides, cudaStream_t s) {
@@ -112,6 +137,13 @@ cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_d
                                  cudaStream_t s) {
     if (B <= 0 || max_det <= 0) return cudaSuccess;
     rescale_batch_kernel<<<dim3(blocks_for((long long)max_det * 12, 256), B), 256, 0, s>>>(det, counts, max_det, params, do_round);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_txt_records(const float* det, const int* counts, int B, int max_det, const float* src_wh, float* rec,
+                               cudaStream_t s) {
+    if (B <= 0 || max_det <= 0) return cudaSuccess;
+    txt_records_kernel<<<dim3(blocks_for(max_det, 128), B), 128, 0, s>>>(det, counts, max_det, src_wh, rec);
     return cudaGetLastError();
 }
 

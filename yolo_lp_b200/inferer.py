@@ -59,3 +59,29 @@ def rescale_table(ori_shapes, target_shapes, device):
     """``[B,5]`` fp32 device table for the fused rescale of ``lp_nms_f32``."""
     return torch.tensor([rescale_params(o, s) for o, s in zip(ori_shapes, target_shapes)],
                         dtype=torch.float64).to(torch.float32).to(device)
+
+
+def txt_records(det, counts, src_shapes):
+    """Batched ``--save-txt`` records of ``Inferer.infer`` (inferer.py:92-93,103-119) for
+    ``det[B,max_det,28]`` (already rescaled + rounded), device ``counts[B]`` and per-image source
+    shapes ``(H0, W0, ...)``: returns ``[B, max_det, 21]`` = 8 class ids | normalised xywh | 8
+    normalised corners | conf (mean of groups 0..6, as the reference reports it)."""
+    B, max_det = det.shape[0], det.shape[1]
+    wh = torch.tensor([[float(s[1]), float(s[0])] for s in src_shapes], dtype=torch.float32).to(det.device)
+    rec = torch.empty((B, max_det, 21), dtype=torch.float32, device=det.device)
+    with torch.cuda.device(det.device):
+        _abi.call("lp_txt_records_f32", det.data_ptr(), counts.data_ptr(), B, max_det, wh.data_ptr(), rec.data_ptr(),
+                  torch.cuda.current_stream(det.device).cuda_stream)
+    return rec
+
+
+def txt_lines(records) -> str:
+    """Text of ``n`` records (host tensor ``[n, 21]``) exactly as ``inferer.py:118-120`` writes it:
+    ``('%g ' * 20).rstrip() % line`` + newline per detection (formatted natively)."""
+    import ctypes
+    r = records.detach().to("cpu", torch.float32).contiguous()
+    n = r.shape[0]
+    buf = ctypes.create_string_buffer(max(64, n * 20 * 16))
+    written = ctypes.c_size_t(0)
+    _abi.call("lp_txt_lines_host", r.data_ptr(), n, buf, len(buf), ctypes.byref(written))
+    return buf.raw[:written.value].decode()
