@@ -411,7 +411,7 @@ def run_ours(args):
             sample = cpu_sample(cfg, cpu_sample_size(args.config))
             cpu_pass(sample, cfg)                      # warm-up
             spent, images, passes = 0.0, 0, 0
-            while spent < 10.0 and passes < 50:
+            while spent < 10.0 and passes < 1000:     # ~10 s of CPU work on the bounded sample
                 dt, n = cpu_pass(sample, cfg)
                 spent, images, passes = spent + dt, images + n, passes + 1
             line["cpu_baseline"] = {
