@@ -19,6 +19,7 @@
  *   lp_rescale_batch_f32     <- same, one launch for a whole [B,max_det,28] batch
  *   lp_detect_postprocess_f32 <- effidehead.py:247-301 + nms.py:31-130 fused (no head tensor)
  *   lp_txt_records_f32 / lp_txt_lines_host <- yolov6/core/inferer.py:92-93,103-120 (--save-txt records)
+ *   lp_eval_match_f32 / lp_eval_accumulate_host <- yolov6/core/evaler.py:153-283 (LP metric)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless the
@@ -204,6 +205,23 @@ LP_API int lp_rescale_batch_f32(float* det, const int* counts, int B, int max_de
 LP_API int lp_txt_records_f32(const float* det, const int* counts, int B, int max_det, const float* src_wh,
                               float* records, lp_stream_t stream);
 LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, size_t buf_bytes, size_t* written);
+
+/*
+ * LP evaluation metric, Evaler.eval (yolov6/core/evaler.py:153-283):
+ *   lp_eval_match_f32        per target (one warp each): box_iou against every prediction of its
+ *                            image (general.py:93-115), first maximum, corner test (:218), 8-character
+ *                            test (:223-226).  targets[T,20] = 8 class ids | xyxy | 8 corners, grouped
+ *                            by image in ascending image order; match[T,4] = t_iou, match index,
+ *                            is_cor, is_cls (t_iou = -1: image without predictions).
+ *   lp_eval_accumulate_host  HOST: the reference's counters (counters[42] = true_cnt, pred_cnt,
+ *                            pred_cnts[10], cor_right[10], cls_right[10], right[10]) and summary[25] =
+ *                            mAP, mAP@.5, mAP@.75, mAP@.5:.95, recall, mAP_list[10], recall_list[10],
+ *                            including the reference's stale-bin quirk for an IoU of exactly 1.0.
+ */
+LP_API int lp_eval_match_f32(const float* det, const int* counts, int B, int max_det, const float* targets,
+                             const int* target_image, int T, float* match, lp_stream_t stream);
+LP_API int lp_eval_accumulate_host(const float* match_host, const int* target_image_host, const int* counts_host, int B,
+                                   int T, long long* counters, double* summary);
 
 #ifdef __cplusplus
 }

@@ -266,3 +266,118 @@ def txt_line(record):
     """The text line of ``inferer.py:118-120``: ``('%g ' * 20).rstrip() % line`` over the first 20 numbers."""
     vals = tuple(float(v) for v in record[:20])
     return ('%g ' * len(vals)).rstrip() % vals
+
+
+# --------------------------------------------------------------------------- LP eval metric
+def box_iou(box1, box2):
+    """``yolov6/utils/general.py:93-115``: [N,4] x [M,4] -> [N,M], fp32,
+    ``inter / ((area1 + area2) - inter)``."""
+    b1, b2 = np.asarray(box1, f32), np.asarray(box2, f32)
+    area1 = ((b1[:, 2] - b1[:, 0]).astype(f32) * (b1[:, 3] - b1[:, 1]).astype(f32)).astype(f32)
+    area2 = ((b2[:, 2] - b2[:, 0]).astype(f32) * (b2[:, 3] - b2[:, 1]).astype(f32)).astype(f32)
+    wh = np.clip((np.minimum(b1[:, None, 2:4], b2[None, :, 2:4]) - np.maximum(b1[:, None, :2], b2[None, :, :2])).astype(f32),
+                 f32(0), None)
+    inter = (wh[..., 0] * wh[..., 1]).astype(f32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (inter / ((area1[:, None] + area2[None, :]).astype(f32) - inter).astype(f32)).astype(f32)
+
+
+def eval_match(pred, target):
+    """Per-target matching of ``Evaler.eval`` for one image, ``yolov6/core/evaler.py:183-229``.
+    pred [n,28] (NMS rows), target [m,20] = 8 class ids | xyxy | 8 corners.  Returns per target
+    (t_iou fp32, match index, is_cor, is_cls); t_iou = -1 where the image has no predictions."""
+    pred, target = np.asarray(pred, f32), np.asarray(target, f32)
+    m = target.shape[0]
+    t_iou = np.full(m, -1, f32)
+    match = np.zeros(m, np.int64)
+    is_cor = np.zeros(m, bool)
+    is_cls = np.zeros(m, bool)
+    if pred.shape[0] == 0 or m == 0:
+        return t_iou, match, is_cor, is_cls
+    iou = box_iou(pred[:, :4], target[:, 8:12])                       # :189
+    match = iou.argmax(0)                                             # :190 first index on ties
+    t_iou = iou[match, np.arange(m)]
+    for k in range(m):
+        tp, tt = pred[match[k]], target[k]
+        area = ((tt[10] - tt[8]).astype(f32) * (tt[11] - tt[9]).astype(f32)).astype(f32)   # :213
+        d = np.abs((tp[4:12] - tt[12:20]).astype(f32))
+        # torch.sum over 8 contiguous fp32 values (:218): the CPU kernel adds in the fixed order below
+        ssum = torch_like_sum8(d)
+        lhs = (ssum / f32(8)).astype(f32)
+        rhs = (f32(0.1) * np.sqrt(area, dtype=f32)).astype(f32)
+        is_cor[k] = bool(lhs < rhs)
+        is_cls[k] = all(int(tp[20 + i]) == int(tt[i]) for i in range(8))                  # :223-226
+    return t_iou, match, is_cor, is_cls
+
+
+def torch_like_sum8(d):
+    """Sum of 8 fp32 values as ``torch.sum`` computes it on CPU for a short contiguous vector:
+    plain left-to-right accumulation (verified against the goldens)."""
+    s = f32(d[0])
+    for v in d[1:]:
+        s = f32(s + f32(v))
+    return s
+
+
+IOU_LIST = [0.5 + i * 0.05 for i in range(10)]   # evaler.py:160, Python doubles
+
+
+def eval_accumulate(per_image):
+    """Counters of ``Evaler.eval`` (``evaler.py:160-245``) from the per-target matches, in image /
+    target order.  Reproduces the reference's quirks: comparisons of the fp32 IoU against Python
+    doubles happen in fp32; an IoU of exactly 1.0 falls into no bin, so the correctness counters
+    reuse the PREVIOUS target's bin index (``iou_idx`` is a stale loop variable) and ``pred_cnts``
+    skips it.  ``per_image``: list of (n_pred, t_iou, is_cor, is_cls)."""
+    lo = [f32(v) for v in IOU_LIST]
+    hi = [f32(v + 0.05) for v in IOU_LIST]
+    c = dict(true_cnt=0, pred_cnt=0, pred_cnts=[0] * 10, cor_right=[0] * 10, cls_right=[0] * 10, right=[0] * 10)
+    iou_idx = None
+    for n_pred, t_iou, is_cor, is_cls in per_image:
+        c["true_cnt"] += len(t_iou)
+        if n_pred == 0 or len(t_iou) == 0:
+            continue
+        for k in range(len(t_iou)):
+            v = f32(t_iou[k])
+            if v < f32(0.5):
+                continue
+            if v >= f32(0.7):
+                c["pred_cnt"] += 1
+            for n in range(10):
+                if v >= lo[n] and v < hi[n]:
+                    iou_idx = n
+                    break
+            if iou_idx is None:
+                raise NameError("iou_idx")   # the reference raises here too
+            if is_cor[k]:
+                c["cor_right"][iou_idx] += 1
+            if is_cls[k]:
+                c["cls_right"][iou_idx] += 1
+            if is_cor[k] and is_cls[k]:
+                c["right"][iou_idx] += 1
+        for k in range(len(t_iou)):
+            v = f32(t_iou[k])
+            if v < f32(0.5):
+                continue
+            for n in range(10):
+                if v >= lo[n] and v < hi[n]:
+                    c["pred_cnts"][n] += 1
+                    break
+    return c
+
+
+def eval_summary(c):
+    """mAP / recall figures of ``evaler.py:247-283`` from the counters (Python doubles)."""
+    right, pred_cnts = c["right"], c["pred_cnts"]
+    mAP_list = [right[i] / pred_cnts[i] if pred_cnts[i] > 0 else -int(right[i] == pred_cnts[i]) for i in range(10)]
+    valid = [v for v in mAP_list if v != -1]
+    mAP_50_95 = sum(valid) / len(valid) if valid else 0.0
+    right_50, pred_50 = sum(right), sum(pred_cnts)
+    right_75 = sum(right[i] for i in range(10) if IOU_LIST[i] >= 0.75)
+    pred_75 = sum(pred_cnts[i] for i in range(10) if IOU_LIST[i] >= 0.75)
+    t_right = sum(right[i] for i in range(10) if IOU_LIST[i] >= 0.7)
+    mAP_50 = right_50 / pred_50 if pred_50 > 0 else 0.0
+    mAP_75 = right_75 / pred_75 if pred_75 > 0 else 0.0
+    mAP = t_right / c["pred_cnt"] if c["pred_cnt"] > 0 else 0.0
+    recall_list = [sum(right[: i + 1]) / c["true_cnt"] if c["true_cnt"] > 0 else 0.0 for i in range(10)]
+    recall = sum(right) / c["true_cnt"]
+    return [mAP, mAP_50, mAP_75, mAP_50_95, recall, mAP_list, recall_list]

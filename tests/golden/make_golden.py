@@ -255,7 +255,56 @@ def make_txt():
     save("txt_records", n=np.array(3), **arrays)
 
 
+def make_eval():
+    """LP metric of Evaler.eval (evaler.py:153-283).  yolov6.core.evaler needs pycocotools at import
+    time only (the stock COCO path); a two-class stub on sys.path is enough to import the module and
+    call the unmodified method on a stand-in `self`."""
+    import tempfile
+    import types
+    stub = tempfile.mkdtemp()
+    os.makedirs(os.path.join(stub, "pycocotools"))
+    open(os.path.join(stub, "pycocotools", "__init__.py"), "w").close()
+    open(os.path.join(stub, "pycocotools", "coco.py"), "w").write("class COCO: pass\n")
+    open(os.path.join(stub, "pycocotools", "cocoeval.py"), "w").write("class COCOeval: pass\n")
+    sys.path.insert(0, stub)
+    from yolov6.core.evaler import Evaler as RefEvaler
+    fake_self = types.SimpleNamespace(eval_speed=lambda task: None)
+
+    g = torch.Generator().manual_seed(11)
+    cfg = synth.CONFIGS[2]
+    n_img = 48
+    preds, targets = [], []
+    for i in range(n_img):
+        x = synth.synth_image(cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], 5, i)
+        det = ref_nms(x[None].clone(), 0.25, 0.45, max_det=300)[0]
+        if i == 7:
+            det = det[:0]                                   # an image without predictions
+        m = int(torch.randint(0, 4, (1,), generator=g)) if i != 3 else 0     # image 3 has no targets
+        m = max(m, 1) if i in (0, 1) else m
+        tgt = torch.zeros((m, 20))
+        for k in range(m):
+            src = det[int(torch.randint(0, max(1, det.shape[0]), (1,), generator=g))] if det.shape[0] else torch.zeros(28)
+            jitter = (torch.rand(4, generator=g) - 0.5) * float(torch.rand(1, generator=g)) * 30.0
+            tgt[k, 8:12] = src[:4] + jitter
+            tgt[k, 12:20] = src[4:12] + (torch.rand(8, generator=g) - 0.5) * float(torch.rand(1, generator=g)) * 40.0
+            tgt[k, :8] = src[20:28]
+            if torch.rand(1, generator=g) < 0.3:
+                tgt[k, int(torch.randint(0, 8, (1,), generator=g))] += 1.0     # one wrong character
+        if i == 5 and m > 0:
+            tgt[0, 8:12] = det[2, :4]                       # IoU exactly 1.0: falls into no bin (stale iou_idx)
+        preds.append(det)
+        targets.append(tgt)
+    # two "batches", as Evaler.predict returns them
+    pb, tb = [preds[:8], preds[8:40], preds[40:]], [targets[:8], targets[8:40], targets[40:]]
+    res = RefEvaler.eval(fake_self, pb, tb, None, "val")
+    arrays = {f"pred{i}": preds[i].numpy() for i in range(n_img)}
+    arrays.update({f"tgt{i}": targets[i].numpy() for i in range(n_img)})
+    save("eval_metric", n=np.array(n_img), split=np.array(8), scalars=np.array(res[:5], np.float64),
+         mAP_list=np.array(res[5], np.float64), recall_list=np.array(res[6], np.float64), **arrays)
+    print("   ", res[:5])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval"]
     for w in which:
         globals()["make_" + w]()

@@ -554,3 +554,23 @@ def test_inferer_flow_nms_rescale_records_end_to_end():
         wrec = lp_oracle.txt_records(rows, src[b])
         assert np.array_equal(rec[b, :k, :20].numpy().view(np.uint32), wrec[:, :20].view(np.uint32))
         assert txt_lines(rec[b, :k]) == "".join(lp_oracle.txt_line(r) + "\n" for r in wrec)
+
+
+# ------------------------------------------------------------------ LP eval metric
+def test_eval_metric_matches_reference_and_oracle():
+    from yolo_lp_b200.evaler import lp_eval, eval_counts
+    g = golden("eval_metric")
+    n, split = int(g["n"]), int(g["split"])
+    preds = [torch.from_numpy(g[f"pred{i}"]).to(DEV) for i in range(n)]
+    targets = [torch.from_numpy(g[f"tgt{i}"]).to(DEV) for i in range(n)]
+    res = lp_eval([preds[:split], preds[split:]], [targets[:split], targets[split:]])   # nested like Evaler.predict
+    assert np.array_equal(np.array(res[:5]), g["scalars"])
+    assert np.array_equal(np.array(res[5]), g["mAP_list"]) and np.array_equal(np.array(res[6]), g["recall_list"])
+    counters, _ = eval_counts(preds, targets)
+    per = []
+    for i in range(n):
+        ti, _m, ic, il = lp_oracle.eval_match(g[f"pred{i}"], g[f"tgt{i}"])
+        per.append((g[f"pred{i}"].shape[0], ti, ic, il))
+    want = lp_oracle.eval_accumulate(per)
+    assert counters[2:12].tolist() == want["pred_cnts"] and counters[32:42].tolist() == want["right"]
+    assert counters[12:22].tolist() == want["cor_right"] and counters[22:32].tolist() == want["cls_right"]

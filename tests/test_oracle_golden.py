@@ -112,3 +112,51 @@ def test_txt_records_oracle_and_native_formatter():
         assert [lp_oracle.txt_line(r) for r in rec] == lines
         assert txt_lines(torch.from_numpy(want)) == "".join(l + "\n" for l in lines)
     assert txt_lines(torch.zeros((0, 21))) == ""
+
+
+def _eval_case():
+    g = golden("eval_metric")
+    n = int(g["n"])
+    return g, [g[f"pred{i}"] for i in range(n)], [g[f"tgt{i}"] for i in range(n)]
+
+
+def test_eval_metric_oracle_matches_reference():
+    """Evaler.eval (evaler.py:153-283) run by the reference on 48 images (empty predictions, empty
+    targets, wrong characters, loose corners, an IoU of exactly 1.0 -> stale bin index)."""
+    g, preds, targets = _eval_case()
+    per = []
+    for p, t in zip(preds, targets):
+        ti, _m, ic, il = lp_oracle.eval_match(p, t)
+        per.append((p.shape[0], ti, ic, il))
+    res = lp_oracle.eval_summary(lp_oracle.eval_accumulate(per))
+    assert np.array_equal(np.array(res[:5]), g["scalars"])
+    assert np.array_equal(np.array(res[5], float), g["mAP_list"])
+    assert np.array_equal(np.array(res[6]), g["recall_list"])
+
+
+def test_eval_accumulate_host_matches_oracle_counters():
+    """The native host accumulator (lp_eval_accumulate_host, no GPU) on oracle matches."""
+    import ctypes
+    from yolo_lp_b200 import _abi, build
+    build.build()
+    g, preds, targets = _eval_case()
+    per, rows, timg = [], [], []
+    for b, (p, t) in enumerate(zip(preds, targets)):
+        ti, m, ic, il = lp_oracle.eval_match(p, t)
+        per.append((p.shape[0], ti, ic, il))
+        for k in range(len(ti)):
+            rows.append([ti[k], m[k], float(ic[k]), float(il[k])])
+            timg.append(b)
+    want = lp_oracle.eval_accumulate(per)
+    match = np.array(rows, np.float32).reshape(-1, 4)
+    timg = np.array(timg, np.int32)
+    counts = np.array([p.shape[0] for p in preds], np.int32)
+    counters = np.zeros(42, np.int64)
+    summary = np.zeros(25, np.float64)
+    _abi.call("lp_eval_accumulate_host", match.ctypes.data, timg.ctypes.data, counts.ctypes.data, len(preds), len(timg),
+              counters.ctypes.data, summary.ctypes.data)
+    assert counters[0] == want["true_cnt"] and counters[1] == want["pred_cnt"]
+    assert counters[2:12].tolist() == want["pred_cnts"] and counters[12:22].tolist() == want["cor_right"]
+    assert counters[22:32].tolist() == want["cls_right"] and counters[32:42].tolist() == want["right"]
+    assert np.array_equal(summary[:5], g["scalars"])
+    assert np.array_equal(summary[5:15], g["mAP_list"]) and np.array_equal(summary[15:25], g["recall_list"])

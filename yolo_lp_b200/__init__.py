@@ -25,6 +25,7 @@ _LAZY = {
     "DecodePlan": "head", "PostprocessPlan": "head",
     "rescale": "inferer", "rescale_batch": "inferer", "rescale_table": "inferer",
     "txt_records": "inferer", "txt_lines": "inferer",
+    "lp_eval": "evaler", "eval_counts": "evaler",
     "install": "patch",
 }
 

@@ -530,4 +530,93 @@ LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, 
     return LP_OK;
 }
 
+LP_API int lp_eval_match_f32(const float* det, const int* counts, int B, int max_det, const float* targets,
+                             const int* target_image, int T, float* match, lp_stream_t stream) {
+    if (T == 0) return LP_OK;
+    if (!det || !counts || !targets || !target_image || !match) return LP_E_NULL;
+    if (B <= 0 || max_det <= 0 || T < 0) return LP_E_SIZE;
+    if (!aligned(det, 16)) return LP_E_ALIGN;
+    return (int)launch_eval_match(det, counts, max_det, targets, target_image, T, match, static_cast<cudaStream_t>(stream));
+}
+
+// Counters and summary of Evaler.eval (yolov6/core/evaler.py:160-283) from the per-target matches,
+// in image / target order.  Quirks kept: the fp32 IoU is compared against the Python doubles
+// 0.5 + 0.05 n rounded to fp32; an IoU that falls into no bin (exactly 1.0) reuses the previous
+// target's bin for the correctness counters (stale `iou_idx`) and is skipped by pred_cnts.
+LP_API int lp_eval_accumulate_host(const float* match_host, const int* target_image_host, const int* counts_host, int B,
+                                   int T, long long* counters, double* summary) {
+    if ((T > 0 && (!match_host || !target_image_host)) || !counts_host || !counters || !summary) return LP_E_NULL;
+    if (B <= 0 || T < 0) return LP_E_SIZE;
+    double iou_list[10];
+    float lo[10], hi[10];
+    for (int n = 0; n < 10; ++n) {
+        iou_list[n] = 0.5 + n * 0.05;
+        lo[n] = (float)iou_list[n];
+        hi[n] = (float)(iou_list[n] + 0.05);
+    }
+    long long true_cnt = 0, pred_cnt = 0, pred_cnts[10] = {0}, cor_right[10] = {0}, cls_right[10] = {0}, right[10] = {0};
+    int iou_idx = -1;
+    int t = 0;
+    while (t < T) {
+        const int b = target_image_host[t];
+        if (b < 0 || b >= B) return LP_E_ARG;
+        int e = t;
+        while (e < T && target_image_host[e] == b) ++e;
+        if (e < T && target_image_host[e] < b) return LP_E_ARG;  // must be grouped in image order
+        true_cnt += e - t;
+        if (counts_host[b] > 0) {
+            for (int k = t; k < e; ++k) {
+                const float v = match_host[4 * k];
+                if (v < 0.5f) continue;
+                if (v >= 0.7f) ++pred_cnt;
+                for (int n = 0; n < 10; ++n)
+                    if (v >= lo[n] && v < hi[n]) { iou_idx = n; break; }
+                if (iou_idx < 0) return LP_E_ARG;  // the reference raises NameError here
+                const bool is_cor = match_host[4 * k + 2] != 0.0f, is_cls = match_host[4 * k + 3] != 0.0f;
+                if (is_cor) ++cor_right[iou_idx];
+                if (is_cls) ++cls_right[iou_idx];
+                if (is_cor && is_cls) ++right[iou_idx];
+            }
+            for (int k = t; k < e; ++k) {
+                const float v = match_host[4 * k];
+                if (v < 0.5f) continue;
+                for (int n = 0; n < 10; ++n)
+                    if (v >= lo[n] && v < hi[n]) { ++pred_cnts[n]; break; }
+            }
+        }
+        t = e;
+    }
+    counters[0] = true_cnt;
+    counters[1] = pred_cnt;
+    for (int n = 0; n < 10; ++n) {
+        counters[2 + n] = pred_cnts[n];
+        counters[12 + n] = cor_right[n];
+        counters[22 + n] = cls_right[n];
+        counters[32 + n] = right[n];
+    }
+    // evaler.py:247-283
+    double m5095 = 0.0;
+    long long valid = 0, right_50 = 0, pred_50 = 0, right_75 = 0, pred_75 = 0, t_right = 0;
+    for (int i = 0; i < 10; ++i) {
+        const double m = pred_cnts[i] > 0 ? (double)right[i] / (double)pred_cnts[i] : -(double)(right[i] == pred_cnts[i]);
+        summary[5 + i] = m;
+        if (m != -1.0) { m5095 += m; ++valid; }
+        right_50 += right[i];
+        pred_50 += pred_cnts[i];
+        if (iou_list[i] >= 0.75) { right_75 += right[i]; pred_75 += pred_cnts[i]; }
+        if (iou_list[i] >= 0.7) t_right += right[i];
+    }
+    summary[0] = pred_cnt > 0 ? (double)t_right / (double)pred_cnt : 0.0;
+    summary[1] = pred_50 > 0 ? (double)right_50 / (double)pred_50 : 0.0;
+    summary[2] = pred_75 > 0 ? (double)right_75 / (double)pred_75 : 0.0;
+    summary[3] = valid > 0 ? m5095 / (double)valid : 0.0;
+    long long acc = 0;
+    for (int i = 0; i < 10; ++i) {
+        acc += right[i];
+        summary[15 + i] = true_cnt > 0 ? (double)acc / (double)true_cnt : 0.0;
+    }
+    summary[4] = true_cnt > 0 ? (double)acc / (double)true_cnt : 0.0;  // the reference divides by zero here
+    return LP_OK;
+}
+
 }  // extern "C"

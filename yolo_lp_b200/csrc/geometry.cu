@@ -103,6 +103,61 @@ __global__ void txt_records_kernel(const float* __restrict__ det, const int* __r
     o[20] = __fdiv_rn(s, 7.0f);
 }
 
+// Per-target matching of Evaler.eval (yolov6/core/evaler.py:183-229), one warp per target:
+// IoU of the target box with every prediction of its image (box_iou, general.py:93-115), first
+// maximum (torch.max, :190), then the corner test (:218) and the 8-character test (:223-226)
+// against the matched prediction.  match[t] = { t_iou, match index, is_cor, is_cls };
+// t_iou = -1 marks an image without predictions (the reference skips it, :188).
+__global__ void eval_match_kernel(const float* __restrict__ det, const int* __restrict__ counts, int max_det,
+                                  const float* __restrict__ targets, const int* __restrict__ target_image, int T,
+                                  float* __restrict__ match) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= T) return;
+    const int b = target_image[t];
+    const int n = min(counts[b], max_det);
+    const float* tg = targets + (size_t)t * 20;
+    const float* rows = det + (size_t)b * max_det * OUTW;
+    float* o = match + (size_t)t * 4;
+    if (n <= 0) {
+        if (lane == 0) { o[0] = -1.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }
+        return;
+    }
+    const float tx1 = tg[8], ty1 = tg[9], tx2 = tg[10], ty2 = tg[11];
+    const float tarea = __fmul_rn(__fsub_rn(tx2, tx1), __fsub_rn(ty2, ty1));
+    float best = -INFINITY;
+    int bi = 1 << 30;
+    for (int i = lane; i < n; i += 32) {
+        const float4 p = *reinterpret_cast<const float4*>(rows + (size_t)i * OUTW);
+        const float parea = __fmul_rn(__fsub_rn(p.z, p.x), __fsub_rn(p.w, p.y));
+        const float w = fmaxf(__fsub_rn(fminf(p.z, tx2), fmaxf(p.x, tx1)), 0.0f);
+        const float h = fmaxf(__fsub_rn(fminf(p.w, ty2), fmaxf(p.y, ty1)), 0.0f);
+        const float inter = __fmul_rn(w, h);
+        const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(parea, tarea), inter));
+        if (iou > best) { best = iou; bi = i; }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {  // max, ties -> lowest index (torch.max on CPU)
+        const float ov = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) {
+        if (bi >= n) bi = 0;  // every IoU was NaN: torch.max returns index 0
+        const float* pr = rows + (size_t)bi * OUTW;
+        float s = fabsf(__fsub_rn(pr[4], tg[12]));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) s = __fadd_rn(s, fabsf(__fsub_rn(pr[4 + i], tg[12 + i])));
+        const bool is_cor = __fdiv_rn(s, 8.0f) < __fmul_rn(0.1f, __fsqrt_rn(tarea));
+        bool is_cls = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) is_cls = is_cls && ((int)pr[20 + i] == (int)tg[i]);
+        o[0] = best;
+        o[1] = (float)bi;
+        o[2] = is_cor ? 1.0f : 0.0f;
+        o[3] = is_cls ? 1.0f : 0.0f;
+    }
+}
+
 static inline unsigned blocks_for(long long n, int t) { return (unsigned)((n + t - 1) / t); }
 
 cudaError_t launch_anchors(const AnchorLevels& lv, float* points, float* strides, cudaStream_t s) {
@@ -137,6 +192,13 @@ cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_d
                                  cudaStream_t s) {
     if (B <= 0 || max_det <= 0) return cudaSuccess;
     rescale_batch_kernel<<<dim3(blocks_for((long long)max_det * 12, 256), B), 256, 0, s>>>(det, counts, max_det, params, do_round);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval_match(const float* det, const int* counts, int max_det, const float* targets,
+                              const int* target_image, int T, float* match, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    eval_match_kernel<<<blocks_for((long long)T * 32, 128), 128, 0, s>>>(det, counts, max_det, targets, target_image, T, match);
     return cudaGetLastError();
 }
 
