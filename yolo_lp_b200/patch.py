@@ -7,6 +7,7 @@ resolved at import time:
   yolov6.core.inferer (inferer.py:20) and yolov6.core.evaler (evaler.py:16)
   yolov6.core.inferer.Inferer.rescale         (staticmethod, inferer.py:203)
   yolov6.models.effidehead.Detect.forward     (eval branch only, effidehead.py:214)
+  yolov6.core.evaler.Evaler.eval              (the LP metric, evaler.py:153; only if the module imports)
 
 Training code paths (losses, assigners, the train branch of ``Detect.forward``
 and of ``generate_anchors``) are left untouched.
@@ -16,7 +17,7 @@ from __future__ import annotations
 import importlib
 
 
-def install(nms: bool = True, rescale: bool = True, detect: bool = True) -> list:
+def install(nms: bool = True, rescale: bool = True, detect: bool = True, evaler: bool = True) -> list:
     """Returns the list of patched ``module.attribute`` names."""
     from . import head, inferer as _rescale, nms as _nms
     done = []
@@ -48,6 +49,19 @@ def install(nms: bool = True, rescale: bool = True, detect: bool = True) -> list
 
             eff.Detect.forward = forward
             done.append("yolov6.models.effidehead.Detect.forward")
+        except Exception:
+            pass
+    if evaler:
+        try:
+            ev = importlib.import_module("yolov6.core.evaler")   # needs pycocotools at import time
+            from .evaler import lp_eval
+
+            def eval_(self, preds, targets, model, task):
+                self.eval_speed(task)                              # evaler.py:155, unchanged
+                return lp_eval(preds, targets)
+
+            ev.Evaler.eval = eval_
+            done.append("yolov6.core.evaler.Evaler.eval")
         except Exception:
             pass
     return done
