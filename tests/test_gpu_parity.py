@@ -574,3 +574,39 @@ def test_eval_metric_matches_reference_and_oracle():
     want = lp_oracle.eval_accumulate(per)
     assert counters[2:12].tolist() == want["pred_cnts"] and counters[32:42].tolist() == want["right"]
     assert counters[12:22].tolist() == want["cor_right"] and counters[22:32].tolist() == want["cls_right"]
+
+
+# ------------------------------------------------------------------ repeatability / multi-device driver
+@pytest.mark.parametrize("cid,B", [(4, 8), (5, 4), (2, 16)])
+def test_repeated_runs_are_bitwise_identical(cid, B):
+    """Race hunt (compute-sanitizer is closed on this pool): the dense configs exercise the
+    histogram segments, several windows and the replica / chunk barriers of K2; 40 back-to-back
+    runs, alternating between two workspaces, must reproduce the first result bit for bit."""
+    cfg = synth.CONFIGS[cid]
+    pred = synth.synth_head(B, cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"]).to(DEV)
+    plans = [NmsPlan(B, cfg["A"], cfg["max_det"], torch.device(DEV), want_anchor=True) for _ in range(2)]
+    out0, cnt0 = plans[0].run(pred, cfg["conf"], cfg["iou"])
+    out0, cnt0, idx0 = out0.clone(), cnt0.clone(), plans[0].kept_anchor.clone()
+    ks = cnt0.cpu().tolist()
+    for it in range(40):
+        plan = plans[it & 1]
+        out, cnt = plan.run(pred, cfg["conf"], cfg["iou"])
+        assert torch.equal(cnt, cnt0), f"run {it}: counts differ"
+        for b, k in enumerate(ks):
+            assert torch.equal(plan.kept_anchor[b, :k], idx0[b, :k]), f"run {it}: kept anchors of image {b} differ"
+            assert torch.equal(out[b, :k], out0[b, :k]), f"run {it}: rows of image {b} differ"
+
+
+def test_sharded_driver_concatenates_in_image_order():
+    from yolo_lp_b200.shard import ShardedNms
+    n_dev = torch.cuda.device_count()
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]      # one GPU: two shards on the same device
+    B = 7
+    pred = synth.synth_head(B, 2100, 320, 8, 100, seed=81)
+    want = lp_oracle.non_max_suppression(pred.numpy(), 0.2, 0.45)
+    drv = ShardedNms(B, 2100, 300, devices=devices)
+    shards = [pred[lo:hi].to(f"cuda:{d}") for d, (lo, hi) in zip(devices, drv.ranges)]
+    got = drv.run(shards, 0.2, 0.45)
+    assert len(got) == B
+    for b in range(B):
+        assert_rows_equal(got[b].numpy(), want[b], f"shard[{b}]")
