@@ -218,6 +218,10 @@ LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, 
  *                            mAP, mAP@.5, mAP@.75, mAP@.5:.95, recall, mAP_list[10], recall_list[10],
  *                            including the reference's stale-bin quirk for an IoU of exactly 1.0.
  */
+/* Label prep of Evaler.predict (evaler.py:119-127): targets[T,21] = image | 8 ids | normalised xywh | 8
+ * normalised corners -> out[T,20] = 8 ids | xyxy px | 8 corners px (same row order), out_image[T]. */
+LP_API int lp_prepare_targets_f32(const float* targets, int T, float w, float h, float* out, int* out_image,
+                                  lp_stream_t stream);
 LP_API int lp_eval_match_f32(const float* det, const int* counts, int B, int max_det, const float* targets,
                              const int* target_image, int T, float* match, lp_stream_t stream);
 LP_API int lp_eval_accumulate_host(const float* match_host, const int* target_image_host, const int* counts_host, int B,

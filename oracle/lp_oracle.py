@@ -381,3 +381,20 @@ def eval_summary(c):
     recall_list = [sum(right[: i + 1]) / c["true_cnt"] if c["true_cnt"] > 0 else 0.0 for i in range(10)]
     recall = sum(right) / c["true_cnt"]
     return [mAP, mAP_50, mAP_75, mAP_50_95, recall, mAP_list, recall_list]
+
+
+def prepare_targets(targets, w, h, batch_size):
+    """Label prep of ``Evaler.predict``, ``yolov6/core/evaler.py:119-127``: ``targets[T,21]`` =
+    image index | 8 class ids | normalised xywh | 8 normalised corners  ->  per image ``[m,20]`` =
+    8 class ids | xyxy (pixels of the letterboxed batch) | 8 corners (pixels)."""
+    t = np.array(targets, f32, copy=True)
+    if t.shape[0]:
+        t[:, 9:13] = xywh2xyxy(t[:, 9:13])                      # :120
+        for j in range(9, 21, 2):                               # :123-125
+            t[:, j] = (t[:, j] * f32(w)).astype(f32)
+            t[:, j + 1] = (t[:, j + 1] * f32(h)).astype(f32)
+    out = [np.zeros((0, 20), f32) for _ in range(batch_size)]
+    for row in t:                                               # :126, order preserved per image
+        b = int(row[0])
+        out[b] = np.concatenate([out[b], row[None, 1:]], 0)
+    return out

@@ -304,7 +304,31 @@ def make_eval():
     print("   ", res[:5])
 
 
+def make_targets():
+    """Label prep of Evaler.predict (evaler.py:119-127), inline in the reference: the statements are
+    replayed here with the reference's own xywh2xyxy."""
+    from yolov6.utils.nms import xywh2xyxy as ref_xywh2xyxy
+    g = torch.Generator().manual_seed(21)
+    bs, w, h = 6, 640, 384
+    T = 17
+    targets = torch.zeros((T, 21))
+    targets[:, 0] = torch.tensor([0, 0, 1, 3, 3, 3, 4, 4, 5, 5, 5, 5, 0, 1, 2, 2, 4]).float()   # not sorted by image
+    targets[:, 1:9] = torch.randint(0, 37, (T, 8), generator=g).float()
+    targets[:, 9:13] = torch.rand((T, 4), generator=g)
+    targets[:, 13:21] = torch.rand((T, 8), generator=g)
+    src = targets.clone()
+    targets[:, 9:13] = ref_xywh2xyxy(targets[:, 9:13])                                   # :120
+    batch_targets = [torch.zeros((0, 20))] * bs                                          # :121
+    for target in targets:                                                               # :122
+        for j in range(9, 21, 2):
+            target[j] = target[j] * w
+            target[j + 1] = target[j + 1] * h
+        batch_targets[int(target[0])] = torch.cat((batch_targets[int(target[0])], target[None, 1:]), dim=0)
+    arrays = {f"out{i}": batch_targets[i].numpy() for i in range(bs)}
+    save("eval_targets", targets=src.numpy(), w=np.array(w), h=np.array(h), bs=np.array(bs), **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets"]
     for w in which:
         globals()["make_" + w]()

@@ -610,3 +610,12 @@ def test_sharded_driver_concatenates_in_image_order():
     assert len(got) == B
     for b in range(B):
         assert_rows_equal(got[b].numpy(), want[b], f"shard[{b}]")
+
+
+def test_prepare_targets_matches_reference():
+    from yolo_lp_b200.evaler import prepare_targets
+    g = golden("eval_targets")
+    out = prepare_targets(torch.from_numpy(g["targets"]).to(DEV), int(g["w"]), int(g["h"]), int(g["bs"]))
+    assert len(out) == int(g["bs"])
+    for i, o in enumerate(out):
+        assert np.array_equal(o.cpu().numpy().view(np.uint32), g[f"out{i}"].view(np.uint32)), i

@@ -160,3 +160,10 @@ def test_eval_accumulate_host_matches_oracle_counters():
     assert counters[22:32].tolist() == want["cls_right"] and counters[32:42].tolist() == want["right"]
     assert np.array_equal(summary[:5], g["scalars"])
     assert np.array_equal(summary[5:15], g["mAP_list"]) and np.array_equal(summary[15:25], g["recall_list"])
+
+
+def test_prepare_targets_oracle():
+    g = golden("eval_targets")
+    out = lp_oracle.prepare_targets(g["targets"], int(g["w"]), int(g["h"]), int(g["bs"]))
+    for i, o in enumerate(out):
+        assert np.array_equal(o.view(np.uint32), g[f"out{i}"].view(np.uint32)), i

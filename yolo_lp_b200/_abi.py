@@ -62,6 +62,7 @@ SIGNATURES = {
                                c_int, c_void_p]),
     "lp_txt_records_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "lp_txt_lines_host": (c_int, [c_void_p, c_longlong, ctypes.c_char_p, c_size_t, POINTER(c_size_t)]),
+    "lp_prepare_targets_f32": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]),
     "lp_eval_match_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "lp_eval_accumulate_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "lp_rescale_batch_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

@@ -530,6 +530,14 @@ LP_API int lp_txt_lines_host(const float* records_host, long long n, char* buf, 
     return LP_OK;
 }
 
+LP_API int lp_prepare_targets_f32(const float* targets, int T, float w, float h, float* out, int* out_image,
+                                  lp_stream_t stream) {
+    if (T == 0) return LP_OK;
+    if (!targets || !out || !out_image) return LP_E_NULL;
+    if (T < 0) return LP_E_SIZE;
+    return (int)launch_prepare_targets(targets, T, w, h, out, out_image, static_cast<cudaStream_t>(stream));
+}
+
 LP_API int lp_eval_match_f32(const float* det, const int* counts, int B, int max_det, const float* targets,
                              const int* target_image, int T, float* match, lp_stream_t stream) {
     if (T == 0) return LP_OK;

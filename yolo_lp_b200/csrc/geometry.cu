@@ -103,6 +103,24 @@ __global__ void txt_records_kernel(const float* __restrict__ det, const int* __r
     o[20] = __fdiv_rn(s, 7.0f);
 }
 
+// Label prep of Evaler.predict (yolov6/core/evaler.py:119-127), one thread per target row:
+// in[T,21] = image | 8 ids | normalised xywh | 8 normalised corners; out[T,20] = 8 ids | xyxy px | corners px.
+// Rows keep their input order; out_image[T] carries the image index for the host-side grouping.
+__global__ void prepare_targets_kernel(const float* __restrict__ in, int T, float w, float h, float* __restrict__ out,
+                                       int* __restrict__ out_image) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const float* r = in + (size_t)t * 21;
+    float* o = out + (size_t)t * 20;
+    out_image[t] = (int)r[0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = r[1 + i];
+    const float4 b = xywh_to_xyxy(r[9], r[10], r[11], r[12]);                      // :120 (nms.py:21-28)
+    o[8] = __fmul_rn(b.x, w); o[9] = __fmul_rn(b.y, h); o[10] = __fmul_rn(b.z, w); o[11] = __fmul_rn(b.w, h);   // :123-125
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[12 + i] = __fmul_rn(r[13 + i], (i & 1) ? h : w);
+}
+
 // Per-target matching of Evaler.eval (yolov6/core/evaler.py:183-229), one warp per target:
 // IoU of the target box with every prediction of its image (box_iou, general.py:93-115), first
 // maximum (torch.max, :190), then the corner test (:218) and the 8-character test (:223-226)
@@ -192,6 +210,12 @@ cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_d
                                  cudaStream_t s) {
     if (B <= 0 || max_det <= 0) return cudaSuccess;
     rescale_batch_kernel<<<dim3(blocks_for((long long)max_det * 12, 256), B), 256, 0, s>>>(det, counts, max_det, params, do_round);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prepare_targets(const float* in, int T, float w, float h, float* out, int* out_image, cudaStream_t s) {
+    if (T <= 0) return cudaSuccess;
+    prepare_targets_kernel<<<blocks_for(T, 128), 128, 0, s>>>(in, T, w, h, out, out_image);
     return cudaGetLastError();
 }
 

@@ -66,3 +66,20 @@ def lp_eval(preds, targets, device=None):
     _, s = eval_counts(preds, targets, device)
     s = s.tolist()
     return [s[0], s[1], s[2], s[3], s[4], s[5:15], s[15:25]]
+
+
+def prepare_targets(targets, w, h, batch_size):
+    """Label prep of ``Evaler.predict`` (``evaler.py:119-127``): ``targets[T,21]`` (CUDA; image index |
+    8 class ids | normalised xywh | 8 normalised corners) -> list of ``batch_size`` tensors ``[m,20]``
+    (8 class ids | xyxy in pixels | 8 corners in pixels), rows of an image in their input order."""
+    if not isinstance(targets, torch.Tensor) or targets.device.type != "cuda":
+        raise RuntimeError("yolo_lp_b200.evaler.prepare_targets needs a CUDA tensor (no CPU fallback)")
+    t = targets.to(torch.float32).contiguous()
+    T = t.shape[0]
+    out = torch.empty((T, 20), dtype=torch.float32, device=t.device)
+    img = torch.empty((T,), dtype=torch.int32, device=t.device)
+    with torch.cuda.device(t.device):
+        _abi.call("lp_prepare_targets_f32", t.data_ptr(), T, float(w), float(h), out.data_ptr(), img.data_ptr(),
+                  torch.cuda.current_stream(t.device).cuda_stream)
+    img = img.long()
+    return [out[img == b] for b in range(batch_size)]   # boolean mask keeps the input order
