@@ -22,6 +22,9 @@
 //         box / corner columns are computed by one thread per position.
 //   out   the tile's rows are contiguous in the output: one TMA bulk store (UBLKCP) when the
 //         destination is 16-byte aligned, coalesced 64-bit stores otherwise.
+// Measured decomposition (B=32 @640^2): loads alone 56 us, + transposition 109 us, + stores 123 us,
+// against 95 us for a pure copy of the same bytes.  A conflict-free 291-pitch tile written out with
+// ordinary coalesced stores instead of the bulk store was slower (142 us).
 #include "level_tiles.cuh"
 
 namespace lp {
