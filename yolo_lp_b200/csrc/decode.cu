@@ -17,8 +17,9 @@
 //         (111 KB in flight per SM).  (One TMA bulk copy per row was measured first: the TMA unit
 //         serialises such small requests at ~100 cycles each, 4x slower than the LSU path.)
 //         Shapes whose rows are not 16-byte aligned (h*w % 4 != 0) use 4-byte cp.async instead.
-//   xpose lanes run along positions: conflict-free reads of the stage, sigmoid, row-major write
-//         into the finished-row tile (row pitch 290 words -> 2-way conflict, accepted);
+//   xpose lanes run along positions: conflict-free reads of the stage, sigmoid, row-major 64-bit
+//         writes (two columns per lane: conflict-free with the packed 290-word pitch) into the
+//         finished-row tile;
 //         box / corner columns are computed by one thread per position.
 //   out   the tile's rows are contiguous in the output: one TMA bulk store (UBLKCP) when the
 //         destination is 16-byte aligned, coalesced 64-bit stores otherwise.
@@ -81,10 +82,19 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
         __syncthreads();                  // ... and everybody else's copies
 
         // class columns: lanes along positions (conflict-free stage reads), sigmoid, transposed write
+        // Two adjacent columns per lane and one 64-bit store: with the packed 290-word row pitch a
+        // 32-bit store per lane is a 2-way bank conflict (290 = 2 mod 32), a 64-bit one is conflict-free
+        // (145 = 1 mod 16 eight-byte units per half-warp phase) and halves the store count.
         if (lane < t.n) {
             float* orow = outt + lane * ROW;
 #pragma unroll 4
-            for (int col = 13 + warp; col < ROW; col += DEC_WARPS) orow[col] = sigmoid_f32(stage[col * DEC_TILE + lane]);
+            for (int col = 14 + 2 * warp; col < ROW; col += 2 * DEC_WARPS) {
+                float2 v;
+                v.x = sigmoid_f32(stage[col * DEC_TILE + lane]);
+                v.y = sigmoid_f32(stage[(col + 1) * DEC_TILE + lane]);
+                *reinterpret_cast<float2*>(orow + col) = v;
+            }
+            if (warp == 0) orow[13] = sigmoid_f32(stage[13 * DEC_TILE + lane]);
         }
         // box / objectness / corner columns: one thread per position
         if (warp == DEC_WARPS - 1 && lane < t.n) {
