@@ -112,7 +112,8 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
                                void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                const float* rescale, int do_round, lp_stream_t stream);
 
-/* Tuning (process-global, not thread-safe): key 0 = upper bound on the CTAs of K1, 0 = one per SM. */
+/* Tuning (process-global, not thread-safe): key 0 = upper bound on the CTAs of K1 / KF (0 = default
+ * heuristic); key 1 = 0 forces the cp.async load path of the decode kernel instead of TMA boxes. */
 LP_API int lp_tune(int key, int value);
 
 /* Debug only (process-global, not thread-safe): device buffer [B,8] of int64 that K2 fills with

@@ -23,7 +23,10 @@ for h, w in synth.level_shapes(img, img):
     levels.append(lv)
 A = sum(h * w for h, w in synth.level_shapes(img, img))
 out = torch.empty((B, A, 290), device=dev)
+from yolo_lp_b200 import _abi
 from yolo_lp_b200.head import DecodePlan
+if os.environ.get("DEC_TMA") == "0":
+    _abi.call("lp_tune", 1, 0)     # force the cp.async load path
 plan = DecodePlan(levels, (8, 16, 32), out)
 for _ in range(5):
     plan.run()

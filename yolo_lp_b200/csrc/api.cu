@@ -103,9 +103,14 @@ LP_API int lp_debug_nms_timing(long long* buf) {
 // bound on the CTAs of K1 (0 = one per SM).  Leaving some SMs to K2 lets the NMS of batch i overlap
 // the filter of batch i+1 when the two stages are driven from two streams.
 static int g_filter_cta_limit = 0;
+static int g_decode_tma = 1;   // key 1: 0 = force the cp.async load path of the decode kernel
 LP_API int lp_tune(int key, int value) {
     if (key == 0 && value >= 0) {
         g_filter_cta_limit = value;
+        return LP_OK;
+    }
+    if (key == 1) {
+        g_decode_tma = value != 0;
         return LP_OK;
     }
     return LP_E_ARG;
@@ -257,6 +262,45 @@ LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double
                                kept_anchor, rescale, do_round, stream);
 }
 
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        tried = true;
+    }
+    return fn;
+}
+
+// tensor maps of every level tensor for the decode kernel's TMA mode; false -> use the cp.async modes
+static bool build_decode_maps(const DecodeLevel (&lv)[LP_MAX_LEVELS], int n_levels, int B, DecodeMaps& maps) {
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return false;
+    for (int l = 0; l < n_levels; ++l) {
+        for (int k = 0; k < DEC_TENSORS; ++k) {
+            const int C = k == 8 ? 4 : k == 9 ? 8 : group_begin(k + 1) - group_begin(k);
+            const float* base = k == 8 ? lv[l].reg : k == 9 ? lv[l].cor : lv[l].cls[k];
+            const cuuint64_t dims[3] = {(cuuint64_t)lv[l].hw, (cuuint64_t)C, (cuuint64_t)B};
+            const cuuint64_t strides[2] = {(cuuint64_t)lv[l].hw * 4, (cuuint64_t)lv[l].hw * 4 * C};
+            const cuuint32_t box[3] = {(cuuint32_t)DEC_TILE, (cuuint32_t)C, 1};
+            const cuuint32_t estr[3] = {1, 1, 1};
+            if (encode(&maps.m[l][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return false;
+        }
+    }
+    return true;
+}
+
 // validates a level table and lays it out for the kernels (anchor / tile offsets per level)
 static int build_levels(const lp_level_t* levels, int n_levels, int B, DecodeLevel (&lv)[LP_MAX_LEVELS], int& A_out,
                         int& tiles_out, bool& bulk_out) {
@@ -312,7 +356,9 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     p.n_tiles = tiles * B;
     p.bulk_in = bulk ? 1 : 0;
     p.out = out;
-    return (int)launch_decode(p, num_sms_cached(), static_cast<cudaStream_t>(stream));
+    DecodeMaps maps;
+    if (bulk && g_decode_tma && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
+    return (int)launch_decode(p, p.bulk_in == 2 ? &maps : nullptr, num_sms_cached(), static_cast<cudaStream_t>(stream));
 }
 
 LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,

@@ -26,24 +26,12 @@
 // Measured decomposition (B=32 @640^2): loads alone 56 us, + transposition 109 us, + stores 123 us,
 // against 95 us for a pure copy of the same bytes.  A conflict-free 291-pitch tile written out with
 // ordinary coalesced stores instead of the bulk store was slower (142 us).
-#include "level_tiles.cuh"
+#include "decode_tile.cuh"
 
 namespace lp {
 
-constexpr int DEC_THREADS = LT_THREADS;
-constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int DEC_STAGES = 4;
-constexpr int OUT_FLOATS = DEC_TILE * ROW;           // [32 positions][290 columns], double-buffered
 constexpr int DEC_SMEM = (DEC_STAGES * STAGE_FLOATS + 2 * OUT_FLOATS) * 4;
-
-__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodeParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -81,35 +69,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
         if (tid == 0) bulk_wait_read1();
         __syncthreads();                  // ... and everybody else's copies
 
-        // class columns: lanes along positions (conflict-free stage reads), sigmoid, transposed write
-        // Two adjacent columns per lane and one 64-bit store: with the packed 290-word row pitch a
-        // 32-bit store per lane is a 2-way bank conflict (290 = 2 mod 32), a 64-bit one is conflict-free
-        // (145 = 1 mod 16 eight-byte units per half-warp phase) and halves the store count.
-        if (lane < t.n) {
-            float* orow = outt + lane * ROW;
-#pragma unroll 4
-            for (int col = 14 + 2 * warp; col < ROW; col += 2 * DEC_WARPS) {
-                float2 v;
-                v.x = sigmoid_f32(stage[col * DEC_TILE + lane]);
-                v.y = sigmoid_f32(stage[(col + 1) * DEC_TILE + lane]);
-                *reinterpret_cast<float2*>(orow + col) = v;
-            }
-            if (warp == 0) orow[13] = sigmoid_f32(stage[13 * DEC_TILE + lane]);
-        }
-        // box / objectness / corner columns: one thread per position
-        if (warp == DEC_WARPS - 1 && lane < t.n) {
-            const int pos = t.p0 + lane;
-            const int y = pos / lv.w, x = pos - y * lv.w;
-            const float ax = anchor_coord(x), ay = anchor_coord(y);
-            const float sd = lv.stride;
-            const float* st = stage + lane;
-            float* r = outt + lane * ROW;
-            const float4 bx = decode_box(ax, ay, st[0 * DEC_TILE], st[1 * DEC_TILE], st[2 * DEC_TILE], st[3 * DEC_TILE], sd);
-            r[0] = bx.x; r[1] = bx.y; r[2] = bx.z; r[3] = bx.w;
-            r[4] = 1.0f;                                             // effidehead.py:290
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[5 + k] = decode_corner(k, ax, ay, st[(5 + k) * DEC_TILE], sd);
-        }
+        transpose_tile(stage, outt, t, lv, warp, lane);
         fence_proxy_async_smem();  // generic-proxy writes of outt -> visible to the bulk store
         __syncthreads();           // also releases this stage for the copies queued next iteration
 
@@ -140,8 +100,9 @@ cudaError_t launch_sigmoid(const float* in, long long n, float* out, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream) {
+cudaError_t launch_decode(const DecodeParams& p, const DecodeMaps* maps, int num_sms, cudaStream_t stream) {
     if (p.n_tiles <= 0) return cudaSuccess;
+    if (p.bulk_in == 2 && maps != nullptr) return launch_decode_tma(p, *maps, num_sms, stream);
     static_assert(DEC_SMEM <= 227 * 1024, "decode stages exceed shared memory");
     cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
     if (e != cudaSuccess) return e;

@@ -1,5 +1,7 @@
 // Kernel parameter blocks and host-side launchers shared by the translation units of liblpnms.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace lp {
@@ -35,10 +37,16 @@ struct DecodeParams {
     int A;
     int tiles_per_image;
     int n_tiles;      // B * tiles_per_image
-    int bulk_in;      // every channel row is 16-byte aligned: TMA bulk loads
+    int bulk_in;      // 0: 4-byte cp.async (unaligned planes), 1: 16-byte cp.async, 2: 3-D TMA boxes (DecodeMaps)
     float* out;
 };
-cudaError_t launch_decode(const DecodeParams& p, int num_sms, cudaStream_t stream);
+// One tensor map per level and source tensor (0..7 class groups, 8 reg, 9 cor): the [B, C, h*w] tensor
+// seen as a 3-D array (h*w innermost), box = 32 positions x all C channels x 1 image.
+constexpr int DEC_TENSORS = 10;
+struct alignas(64) DecodeMaps {
+    CUtensorMap m[LP_MAX_LEVELS][DEC_TENSORS];
+};
+cudaError_t launch_decode(const DecodeParams& p, const DecodeMaps* maps, int num_sms, cudaStream_t stream);
 cudaError_t launch_sigmoid(const float* in, long long n, float* out, cudaStream_t stream);
 
 // source plane of output column `col` (col != 4) for image b of level lv
