@@ -285,6 +285,26 @@ def test_decode_full_size_vs_oracle():
     np.testing.assert_allclose(got[..., 13:], want[..., 13:], rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("B,H,W", [(32, 640, 640), (3, 1280, 1280), (5, 416, 640), (1, 64, 96), (2, 608, 608)])
+def test_decode_tma_path_equals_lsu_path_and_repeats(B, H, W):
+    """The warp-specialised TMA kernel (decode_tma.cu) and the cp.async kernel (decode.cu, forced with
+    lp_tune(1, 0)) share the arithmetic: bit-identical outputs; 20 repeats of the TMA kernel over a
+    poisoned output catch ring / barrier races.  608x608 has a 19x19 level (rows not 16-byte aligned):
+    both settings then run the 4-byte cp.async path."""
+    from yolo_lp_b200 import _abi
+    levels = synth.synth_levels(B, H, W, DEV, seed=B + H)
+    try:
+        _abi.call("lp_tune", 1, 0)
+        ref = lp.detect_decode(levels, (8, 16, 32)).clone()
+    finally:
+        _abi.call("lp_tune", 1, 1)
+    plan = lp.DecodePlan(levels, (8, 16, 32))
+    for _ in range(20):
+        plan.out.fill_(float("nan"))
+        got = plan.run()
+        assert torch.equal(got.view(torch.int32), ref.view(torch.int32))
+
+
 def test_detect_forward_eval_runs_module_convs_then_kernel():
     """A stand-in module with the reference Detect's attribute names (the reference itself is
     not on the GPU box): convs run in torch, the tail in the kernel."""

@@ -45,6 +45,17 @@ try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     pass
+if os.environ.get("DEC_PROFILE"):   # library built with LPNMS_NVCC_EXTRA=-DLP_DEC_PROFILE
+    buf = torch.zeros((148, 3, 4), dtype=torch.int64, device=dev)
+    _abi.call("lp_debug_nms_timing", buf.data_ptr())
+    plan.run()
+    torch.cuda.synchronize()
+    _abi.call("lp_debug_nms_timing", None)
+    tiles = B * sum((h * w + 31) // 32 for h, w in synth.level_shapes(img, img)) / 148
+    t = (buf.double().mean(0) / tiles).tolist()
+    print("cycles per tile  load producer: other %.0f wait-empty %.0f issue %.0f" % tuple(t[0][:3]))
+    print("                 store producer: other %.0f wait-ofull %.0f issue %.0f wait-read %.0f" % tuple(t[1]))
+    print("                 consumer t0: wait-oempty %.0f wait-full %.0f transposition %.0f release %.0f" % tuple(t[2]))
 print(json.dumps({"kernel": "lp::decode_kernel", "B": B, "img": img, "A": A, "ms": ms, "algorithmic_bytes": algo,
                   "achieved_gbs": algo / ms / 1e6, "frac_of_measured_hbm": algo / ms / 1e6 / peak,
                   "images_per_s": B / ms * 1e3}))

@@ -356,8 +356,9 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     p.n_tiles = tiles * B;
     p.bulk_in = bulk ? 1 : 0;
     p.out = out;
+    p.timing = g_debug_timing;
     DecodeMaps maps;
-    if (bulk && g_decode_tma && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
+    if (bulk && g_decode_tma && aligned(out, 16) && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
     return (int)launch_decode(p, p.bulk_in == 2 ? &maps : nullptr, num_sms_cached(), static_cast<cudaStream_t>(stream));
 }
 

@@ -39,6 +39,7 @@ struct DecodeParams {
     int n_tiles;      // B * tiles_per_image
     int bulk_in;      // 0: 4-byte cp.async (unaligned planes), 1: 16-byte cp.async, 2: 3-D TMA boxes (DecodeMaps)
     float* out;
+    long long* timing;  // debug only (-DLP_DEC_PROFILE builds): per-CTA cycle sums, see decode_tma.cu
 };
 // One tensor map per level and source tensor (0..7 class groups, 8 reg, 9 cor): the [B, C, h*w] tensor
 // seen as a 3-D array (h*w innermost), box = 32 positions x all C channels x 1 image.
