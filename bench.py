@@ -248,10 +248,10 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     del dec, plans, pipe, levels
     torch.cuda.empty_cache()
     return {
-        "decode_kernel": {"kernel": "lp::decode_kernel", "ms": t_dec, "algorithmic_bytes": dec_bytes,
+        "decode_kernel": {"kernel": "lp::decode_tma_kernel", "ms": t_dec, "algorithmic_bytes": dec_bytes,
                           "achieved_gbs": dec_bytes / t_dec / 1e6, "frac_of_hbm_peak": dec_bytes / t_dec / 1e6 / peak},
         "fused_path": {"what": "raw level tensors -> detections (lp_detect_postprocess_f32), no [B,A,290] tensor",
-                       "kf_kernel": "lp::levels_filter_kernel", "kf_ms": t_kf, "kf_algorithmic_bytes": kf_bytes,
+                       "kf_kernel": "lp::levels_filter_tma_kernel", "kf_ms": t_kf, "kf_algorithmic_bytes": kf_bytes,
                        "kf_achieved_gbs": kf_bytes / t_kf / 1e6, "kf_frac_of_hbm_peak": kf_bytes / t_kf / 1e6 / peak,
                        "serial_ms_per_step": t_serial, "pipelined_ms_per_step": t_pipe,
                        "images_per_s_pipelined": B / t_pipe * 1e3, "steps": K}}

@@ -305,6 +305,40 @@ def test_decode_tma_path_equals_lsu_path_and_repeats(B, H, W):
         assert torch.equal(got.view(torch.int32), ref.view(torch.int32))
 
 
+@pytest.mark.parametrize("B,H,W,conf", [(32, 640, 640, 0.25), (40, 640, 640, 0.001), (6, 1280, 1280, 0.25)])
+def test_fused_tma_path_equals_lsu_path_many_tiles_per_cta(B, H, W, conf):
+    """Shapes with dozens of tiles per persistent CTA, so the ring, the per-slot barriers and the
+    producer / scanner / finisher hand-offs of fused_tma.cu all wrap many times.  First run on a
+    poisoned workspace (a cold workspace makes the finishers slow -- that once let a fast finisher
+    take over a barrier that belonged to a slow one), then back-to-back repeats; reference = the
+    register-resident kernel of fused.cu (forced with lp_tune(1, 0)), itself pinned to
+    decode -> K1 -> K2 by test_fused_postprocess_equals_decode_then_nms."""
+    from yolo_lp_b200 import _abi
+    levels = synth.synth_levels(B, H, W, DEV, seed=7)
+    try:
+        _abi.call("lp_tune", 1, 0)
+        ref = lp.PostprocessPlan(levels, (8, 16, 32), 300)
+        ref_out, ref_counts = ref.run(conf, 0.45)
+        torch.cuda.synchronize()
+    finally:
+        _abi.call("lp_tune", 1, 1)
+
+    def same(out, counts):
+        return torch.equal(counts, ref_counts) and all(
+            torch.equal(out[b, :int(counts[b])], ref_out[b, :int(counts[b])]) for b in range(B))
+
+    for poison in (0x00, 0xFF):
+        plan = lp.PostprocessPlan(levels, (8, 16, 32), 300)
+        plan.workspace.fill_(poison)
+        out, counts = plan.run(conf, 0.45)
+        torch.cuda.synchronize()
+        assert same(out, counts), f"first run on a workspace filled with {poison:#x}"
+    for _ in range(10):
+        out, counts = plan.run(conf, 0.45)
+    torch.cuda.synchronize()
+    assert same(out, counts)
+
+
 def test_detect_forward_eval_runs_module_convs_then_kernel():
     """A stand-in module with the reference Detect's attribute names (the reference itself is
     not on the GPU box): convs run in torch, the tail in the kernel."""

@@ -56,6 +56,6 @@ if os.environ.get("DEC_PROFILE"):   # library built with LPNMS_NVCC_EXTRA=-DLP_D
     print("cycles per tile  load producer: other %.0f wait-empty %.0f issue %.0f" % tuple(t[0][:3]))
     print("                 store producer: other %.0f wait-ofull %.0f issue %.0f wait-read %.0f" % tuple(t[1]))
     print("                 consumer t0: wait-oempty %.0f wait-full %.0f transposition %.0f release %.0f" % tuple(t[2]))
-print(json.dumps({"kernel": "lp::decode_kernel", "B": B, "img": img, "A": A, "ms": ms, "algorithmic_bytes": algo,
+print(json.dumps({"kernel": "lp::decode_tma_kernel", "B": B, "img": img, "A": A, "ms": ms, "algorithmic_bytes": algo,
                   "achieved_gbs": algo / ms / 1e6, "frac_of_measured_hbm": algo / ms / 1e6 / peak,
                   "images_per_s": B / ms * 1e3}))

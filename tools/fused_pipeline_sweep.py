@@ -1,5 +1,8 @@
 #!/usr/bin/env python3
-"""Fused path: KF alone / serial step / two-stream pipelined step vs the KF CTA limit (tuning aid)."""
+"""Fused path: KF alone / serial step / two-stream pipelined step vs the KF CTA limit (tuning aid).
+
+    python tools/fused_pipeline_sweep.py [B] [img] [conf] [iou] [cta,cta,...]   (0 = the library's own policy)
+"""
 import os
 import sys
 
@@ -8,7 +11,12 @@ import torch
 from yolo_lp_b200 import _abi, synth
 from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
 
-B, img, conf, iou, K = 32, 640, 0.25, 0.45, 100
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+img = int(sys.argv[2]) if len(sys.argv) > 2 else 640
+conf = float(sys.argv[3]) if len(sys.argv) > 3 else 0.25
+iou = float(sys.argv[4]) if len(sys.argv) > 4 else 0.45
+CTAS = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0, 148, 132, 124, 120, 116, 112, 108, 100]
+K = 100
 dev = torch.device("cuda:0")
 levels = synth.synth_levels(B, img, img, dev, seed=1)
 
@@ -26,7 +34,7 @@ def timed(fn, k=K):
     return a.elapsed_time(b) / k * 1e3
 
 
-for ctas in (0, 148, 140, 132, 124, 116, 100):
+for ctas in CTAS:
     _abi.call("lp_tune", 0, ctas)
     plans = [PostprocessPlan(levels, (8, 16, 32), 300) for _ in range(2)]
     t_kf = timed(lambda: plans[0].run_filter(conf))

@@ -281,11 +281,12 @@ static EncodeTiledFn tensor_map_encoder() {
 }
 
 // tensor maps of every level tensor for the decode kernel's TMA mode; false -> use the cp.async modes
-static bool build_decode_maps(const DecodeLevel (&lv)[LP_MAX_LEVELS], int n_levels, int B, DecodeMaps& maps) {
+static bool build_decode_maps(const DecodeLevel (&lv)[LP_MAX_LEVELS], int n_levels, int B, DecodeMaps& maps,
+                              int n_tensors = DEC_TENSORS) {
     EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) return false;
     for (int l = 0; l < n_levels; ++l) {
-        for (int k = 0; k < DEC_TENSORS; ++k) {
+        for (int k = 0; k < n_tensors; ++k) {
             const int C = k == 8 ? 4 : k == 9 ? 8 : group_begin(k + 1) - group_begin(k);
             const float* base = k == 8 ? lv[l].reg : k == 9 ? lv[l].cor : lv[l].cls[k];
             const cuuint64_t dims[3] = {(cuuint64_t)lv[l].hw, (cuuint64_t)C, (cuuint64_t)B};
@@ -362,8 +363,10 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     return (int)launch_decode(p, p.bulk_in == 2 ? &maps : nullptr, num_sms_cached(), static_cast<cudaStream_t>(stream));
 }
 
-LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
-                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
+// overlapped: the caller runs K2 of another batch concurrently (the pipelined entry and the stand-alone
+// stage entry, which exists for exactly that); false for the serial one-call path
+static int detect_filter(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det, void* workspace,
+                         size_t workspace_bytes, lp_stream_t stream, bool overlapped) {
     if (max_det < 0) return LP_E_SIZE;
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     LevelsFilterParams k;
@@ -392,12 +395,25 @@ LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, d
     k.counts = f.counts;
     k.key_stride = f.key_stride;
     k.tile_counter = f.tile_counter;
-    // like K1: one persistent CTA per SM, some SMs left free for K2 of the previous batch (KF is
-    // latency-bound and wants more SMs than K1: a sixth is the measured sweet spot)
+    k.timing = g_debug_timing;
+    DecodeMaps maps;
+    const bool tma = bulk && g_decode_tma && build_decode_maps(k.lv, n_levels, B, maps, NGROUP);
+    // like K1: one persistent CTA per SM, some SMs left free for K2 of the previous batch.  The
+    // register-resident kernel is latency-bound and wants more SMs than K1 (a sixth left free is the
+    // measured sweet spot; K2's CTAs also fit beside it on a shared SM).  The TMA kernel fills its
+    // SM's shared memory, so K2 only runs on the SMs it leaves: one per image, up to half of them
+    // (measured: B=32 -> 116 CTAs, B=64 -> 84 CTAs are the best pipelined points).  With nothing to
+    // overlap it still runs best a little short of all SMs (B=64: 110 us on 124, 120 us on 148).
     int ctas = num_sms_cached();
-    ctas -= B < ctas / 6 ? B : ctas / 6;
+    const int spare = tma && overlapped ? ctas / 2 : ctas / 6;
+    ctas -= B < spare ? B : spare;
     if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < num_sms_cached() ? g_filter_cta_limit : num_sms_cached();
-    return (int)launch_levels_filter(k, ctas, s);
+    return (int)launch_levels_filter(k, tma ? &maps : nullptr, ctas, s);
+}
+
+LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
+    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, true);
 }
 
 LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
@@ -446,7 +462,7 @@ LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
     if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
     if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
-    rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream);
+    rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, false);
     if (rc != LP_OK) return rc;
     return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
                                   kept_anchor, rescale, do_round, stream);

@@ -9,23 +9,21 @@
 // Algorithmic traffic: 1156 B read + 1160 B written per anchor (the reference moves the payload
 // roughly three times each way through ~30 launches).
 //
+// This is the general-shape kernel: all 512 threads load, transpose and store in turn.  Inputs
+// whose level planes have 16-byte aligned rows (h*w % 4 == 0) take decode_tma.cu instead (TMA box
+// loads + warp specialisation, 0.93 of the measured HBM peak against 0.80 here).
+//
 // HBM-bound transpose, persistent CTAs (one per SM), software-pipelined over tiles of 32 anchor
 // positions of one level of one image:
 //   in    289 channel rows of 32 positions (128 B each) land channel-major in a shared-memory
 //         stage through 16-byte cp.async copies (LDGSTS.128, no register staging) issued by all
 //         threads; four stages, so the loads of tiles t+1..t+3 fly while tile t is transposed
-//         (111 KB in flight per SM).  (One TMA bulk copy per row was measured first: the TMA unit
-//         serialises such small requests at ~100 cycles each, 4x slower than the LSU path.)
-//         Shapes whose rows are not 16-byte aligned (h*w % 4 != 0) use 4-byte cp.async instead.
-//   xpose lanes run along positions: conflict-free reads of the stage, sigmoid, row-major 64-bit
-//         writes (two columns per lane: conflict-free with the packed 290-word pitch) into the
-//         finished-row tile;
-//         box / corner columns are computed by one thread per position.
+//         (111 KB in flight per SM).  Shapes whose rows are not 16-byte aligned use 4-byte cp.async.
+//   xpose transpose_tile (decode_tile.cuh), shared with decode_tma.cu;
 //   out   the tile's rows are contiguous in the output: one TMA bulk store (UBLKCP) when the
 //         destination is 16-byte aligned, coalesced 64-bit stores otherwise.
-// Measured decomposition (B=32 @640^2): loads alone 56 us, + transposition 109 us, + stores 123 us,
-// against 95 us for a pure copy of the same bytes.  A conflict-free 291-pitch tile written out with
-// ordinary coalesced stores instead of the bulk store was slower (142 us).
+// Per-tile phase profile (clock64): ~1400 cycles issuing the loads, ~2000 transposing, ~370 issuing
+// the store, serialised by the two CTA-wide barriers: 3900 cycles against a ~2900-cycle HBM budget.
 #include "decode_tile.cuh"
 
 namespace lp {

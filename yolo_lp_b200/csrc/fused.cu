@@ -13,8 +13,10 @@
 // a lane keeps a whole group (<= 37 independent loads) in flight.  Only the 277 class planes are
 // streamed (1108 B per anchor); box and corner planes are touched for candidates only.
 // Traffic per anchor: 1108 B instead of 1156 + 1160 (decode) + 1160 (K1) = 3476 B.
-// (A variant on the decode kernel's 6-stage cp.async shared-memory ring was measured too: 118 us
-// against 62 us for this register-resident form on the cfg2 shape.)
+// (A variant on the decode kernel's cp.async shared-memory ring was measured too: 118 us against
+// 62 us for this register-resident form on the cfg2 shape.  The TMA-fed, warp-specialised
+// fused_tma.cu is the one that beats it -- 57 us -- and is the default for 16-byte aligned planes;
+// this kernel serves every other shape.)
 //
 // The same pass tracks, per group, the first index of the maximum (torch.max semantics,
 // nms.py:81-88); a surviving lane then decodes its own box and corners (effidehead.py:283-286,
@@ -22,7 +24,7 @@
 // suppress and copy 112-byte records.  The one subtlety -- two different logits rounding to the
 // same sigmoid, where the reference's argmax is the earlier index -- is detected exactly (one more
 // sigmoid per group) and resolved by a rare warp-cooperative pass.
-#include "kernels.cuh"
+#include "fused_tile.cuh"
 
 namespace lp {
 
@@ -50,29 +52,6 @@ __device__ __forceinline__ void group_scan(const float (&v)[37], float& best, in
         arg = up ? c : arg;
         best = up ? v[c] : best;
     }
-}
-
-// Exact first argmax in sigmoid space for one group of one anchor, warp-cooperative (lanes along the
-// group's columns).  Only reached when two different logits round to the same sigmoid.
-__device__ __noinline__ int group_argmax_exact(const float* plane, size_t hw, int width, int lane) {
-    constexpr int kInvalid = 1 << 20;
-    float best = -INFINITY;
-    int bi = kInvalid;
-    if (lane < width) {
-        best = sigmoid_f32(__ldg(plane + (size_t)lane * hw));
-        bi = lane;
-    }
-    if (lane + 32 < width) {
-        const float v = sigmoid_f32(__ldg(plane + (size_t)(lane + 32) * hw));
-        if (v > best) { best = v; bi = lane + 32; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    return bi;
 }
 
 __global__ void __launch_bounds__(KF_THREADS, 1) levels_filter_kernel(const LevelsFilterParams p) {
@@ -119,62 +98,15 @@ __global__ void __launch_bounds__(KF_THREADS, 1) levels_filter_kernel(const Leve
         LP_GROUP(0, 31) LP_GROUP(1, 24) LP_GROUP(2, 37) LP_GROUP(3, 37)
         LP_GROUP(4, 37) LP_GROUP(5, 37) LP_GROUP(6, 37) LP_GROUP(7, 37)
 #undef LP_GROUP
-        float filt, score;
-        lp_means(c, filt, score);
-
-        const bool pass = valid && (filt >= p.conf);
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (m) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(p.counts + b, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-            // rare: resolve sigmoid-space ties exactly, one survivor and group at a time
-            for (unsigned todo = __ballot_sync(0xffffffffu, pass && ties != 0); todo; todo &= todo - 1) {
-                const int src = __ffs(todo) - 1;
-                const int cpos = __shfl_sync(0xffffffffu, pos, src);
-                const unsigned tg = __shfl_sync(0xffffffffu, ties, src);
-#pragma unroll
-                for (int g = 0; g < NGROUP; ++g) {
-                    if (!((tg >> g) & 1u)) continue;  // warp-uniform
-                    const int width = group_begin(g + 1) - group_begin(g);
-                    const int exact = group_argmax_exact(lv.cls[g] + off * width + cpos, hw, width, lane);
-                    if (lane == src) args = (args & ~(63ull << (6 * g))) | ((unsigned long long)exact << (6 * g));
-                }
-            }
-            if (pass) {
-                // this lane finishes its own row: box (nms.py:79 on effidehead.py:283,285), corners (:284,286)
-                const unsigned anchor = (unsigned)(lv.anchor_off + pos);
-                p.keys[(size_t)b * p.key_stride + slot] = make_key(score, anchor);
-                p.slot_of[(size_t)b * p.A + anchor] = slot;
-                const float* reg = lv.reg + off * 4 + pos;
-                const float* cor = lv.cor + off * 8 + pos;
-                const int y = pos / lv.w, x = pos - y * lv.w;
-                const float ax = anchor_coord(x), ay = anchor_coord(y);
-                const float4 q = decode_box(ax, ay, __ldg(reg), __ldg(reg + hw), __ldg(reg + 2 * hw), __ldg(reg + 3 * hw), lv.stride);
-                float4* row = reinterpret_cast<float4*>(p.rec + ((size_t)b * p.A + slot) * OUTW);
-                float k[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) k[i] = decode_corner(i, ax, ay, __ldg(cor + i * hw), lv.stride);
-                row[0] = xywh_to_xyxy(q.x, q.y, q.z, q.w);
-                row[1] = make_float4(k[0], k[1], k[2], k[3]);
-                row[2] = make_float4(k[4], k[5], k[6], k[7]);
-                row[3] = make_float4(c[0], c[1], c[2], c[3]);
-                row[4] = make_float4(c[4], c[5], c[6], c[7]);
-                float a[NGROUP];
-#pragma unroll
-                for (int g = 0; g < NGROUP; ++g) a[g] = (float)(unsigned)((args >> (6 * g)) & 63u);
-                row[5] = make_float4(a[0], a[1], a[2], a[3]);
-                row[6] = make_float4(a[4], a[5], a[6], a[7]);
-            }
-        }
+        finish_tile(p, lv, b, pos, valid, c, args, ties, lane);
         tile = __shfl_sync(0xffffffffu, next, 0);
         if (lane == 0 && tile < p.n_tiles) next = n_warps + (int)atomicAdd(p.tile_counter, 1u);
     }
 }
 
-cudaError_t launch_levels_filter(const LevelsFilterParams& p, int num_ctas, cudaStream_t stream) {
+cudaError_t launch_levels_filter(const LevelsFilterParams& p, const DecodeMaps* maps, int num_ctas, cudaStream_t stream) {
     if (p.n_tiles <= 0) return cudaSuccess;
+    if (maps != nullptr) return launch_levels_filter_tma(p, *maps, num_ctas, stream);
     int grid = (p.n_tiles + KF_WARPS - 1) / KF_WARPS;
     if (grid > num_ctas) grid = num_ctas;
     levels_filter_kernel<<<grid, KF_THREADS, 0, stream>>>(p);

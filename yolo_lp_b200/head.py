@@ -145,7 +145,7 @@ class PostprocessPlan(_LevelTable):
     """Fused head tail + NMS (``lp_detect_postprocess_f32``): raw level tensors -> detections without
     materialising ``[B, A, 290]``.  Bit-identical to ``DecodePlan`` followed by ``NmsPlan``."""
 
-    KERNELS_PER_CALL = 2  # lp::levels_filter_kernel, lp::nms_kernel<true>
+    KERNELS_PER_CALL = 2  # lp::levels_filter_tma_kernel (or lp::levels_filter_kernel), lp::nms_kernel<true>
 
     def __init__(self, levels, strides=(8, 16, 32), max_det: int = 300, max_nms: int = _abi.MAX_NMS,
                  want_anchor: bool = False):
