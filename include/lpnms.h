@@ -126,6 +126,10 @@ LP_API int lp_debug_nms_timing(long long* buf);
  * filtered_event; workspace_free_event (may be NULL) is the done_event of the step that last used
  * this workspace; done_event / time_*_event (may be NULL) are recorded after K2 / round K1.
  * All events are cudaEvent_t handles owned by the caller.
+ * K2 of a pipelined step zeroes the workspace's candidate counters once it has read them; a
+ * non-NULL workspace_free_event therefore also asserts that the LAST operation on this workspace
+ * was such a step, and lets the entry skip the memset node in front of K1.  Pass NULL whenever the
+ * workspace is fresh or was last touched by any other entry point.
  */
 LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
                                 int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,

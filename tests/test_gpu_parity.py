@@ -396,6 +396,13 @@ def test_pipeline_matches_serial_path_on_alternating_batches():
     for which, out, counts in results:
         for b, k in enumerate(counts.cpu().tolist()):
             assert_rows_equal(out[b, :k].cpu().numpy(), wants[which][b], f"pipeline batch {which}[{b}]")
+    # K2 of a pipelined step re-arms the workspace (zeroed candidate counters + tile counter), which is
+    # what lets the next pipelined step on it skip the memset node; any other entry still zeroes itself
+    for plan in pipe.plans:
+        assert int(plan.workspace[: 4 * (plan.B + 1)].view(torch.int32).abs().sum()) == 0
+    out, counts = pipe.plans[0].run(devs[1], 0.15, 0.5)
+    for b, k in enumerate(counts.cpu().tolist()):
+        assert_rows_equal(out[b, :k].cpu().numpy(), wants[1][b], f"serial call on a pipeline workspace [{b}]")
 
 
 def test_filter_cta_limit_does_not_change_results():

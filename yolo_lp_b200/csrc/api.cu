@@ -152,13 +152,16 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
     n.timing = g_debug_timing;
     n.from_levels = 0;
+    n.rearm = 0;
     n.rec = reinterpret_cast<const float*>(ws + w.rec);           // only valid in a fused-size workspace
     n.slot_of = reinterpret_cast<const unsigned*>(ws + w.slot_of);
     return LP_OK;
 }
 
-LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
-                             size_t workspace_bytes, lp_stream_t stream) {
+// armed: the last kernel that ran on this workspace was a K2 launched with rearm (it zeroed the
+// candidate counts and the tile counter), so the memset node in front of the filter kernel is skipped
+static int nms_filter(const float* pred, int B, int A, double conf_thres, void* workspace, size_t workspace_bytes,
+                      lp_stream_t stream, bool armed) {
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     FilterParams f;
     NmsParams n;
@@ -168,8 +171,10 @@ LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres,
     const WsLayout w = ws_layout(B, A, 0);
     if (workspace_bytes < w.kept_box) return LP_E_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);  // counts + tile counter
-    if (e != cudaSuccess) return (int)e;
+    if (!armed) {
+        const cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);  // counts + tile counter
+        if (e != cudaSuccess) return (int)e;
+    }
     f.conf = (float)conf_thres;  // tensor >= python-scalar compares in fp32
     // K1 saturates HBM with roughly half the SMs (one 217 KB CTA each); the rest is left free so
     // that K2 of the previous batch (one CTA per image, driven from a second stream) can run
@@ -180,9 +185,14 @@ LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres,
     return (int)launch_filter(f, ctas, s);
 }
 
-LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
-                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                               const float* rescale, int do_round, lp_stream_t stream) {
+LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
+                             size_t workspace_bytes, lp_stream_t stream) {
+    return nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, stream, false);
+}
+
+static int nms_suppress(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms, void* workspace,
+                        size_t workspace_bytes, float* out, int* counts, int* kept_anchor, const float* rescale,
+                        int do_round, lp_stream_t stream, bool rearm) {
     if (!counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0) return LP_E_SIZE;
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
@@ -201,7 +211,15 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
     n.kept_anchor = kept_anchor;
     n.rescale = rescale;
     n.do_round = do_round;
+    n.rearm = rearm ? 1 : 0;
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
+                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                               const float* rescale, int do_round, lp_stream_t stream) {
+    return nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                        rescale, do_round, stream, false);
 }
 
 LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
@@ -220,7 +238,8 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_begin_event), sf);
         if (e != cudaSuccess) return (int)e;
     }
-    int rc = lp_nms_filter_f32(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream);
+    // a workspace that comes with the done_event of its previous step was re-armed by that step's K2
+    int rc = nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream, workspace_free_event != nullptr);
     if (rc != LP_OK) return rc;
     if (time_end_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
@@ -230,8 +249,8 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
     if (e != cudaSuccess) return (int)e;
     e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
     if (e != cudaSuccess) return (int)e;
-    rc = lp_nms_suppress_f32(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
-                             rescale, do_round, nms_stream);
+    rc = nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                      rescale, do_round, nms_stream, true);
     if (rc != LP_OK) return rc;
     if (done_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
@@ -366,7 +385,7 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
 // overlapped: the caller runs K2 of another batch concurrently (the pipelined entry and the stand-alone
 // stage entry, which exists for exactly that); false for the serial one-call path
 static int detect_filter(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det, void* workspace,
-                         size_t workspace_bytes, lp_stream_t stream, bool overlapped) {
+                         size_t workspace_bytes, lp_stream_t stream, bool overlapped, bool armed = false) {
     if (max_det < 0) return LP_E_SIZE;
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     LevelsFilterParams k;
@@ -382,8 +401,10 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
     const WsLayout w = ws_layout(B, A, max_det);
     if (workspace_bytes < w.total_fused) return LP_E_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
-    if (e != cudaSuccess) return (int)e;
+    if (!armed) {
+        const cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
+        if (e != cudaSuccess) return (int)e;
+    }
     k.A = A;
     k.rec = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.rec);
     k.slot_of = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + w.slot_of);
@@ -416,9 +437,9 @@ LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, d
     return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, true);
 }
 
-LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
-                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream) {
+static int detect_suppress(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det, int max_nms,
+                           void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                           const float* rescale, int do_round, lp_stream_t stream, bool rearm) {
     if (!counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0) return LP_E_SIZE;
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
@@ -443,7 +464,15 @@ LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B,
     n.rescale = rescale;
     n.do_round = do_round;
     n.from_levels = 1;
+    n.rearm = rearm ? 1 : 0;
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
+                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream) {
+    return detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                           kept_anchor, rescale, do_round, stream, false);
 }
 
 LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
@@ -485,7 +514,8 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_begin_event), sf);
         if (e != cudaSuccess) return (int)e;
     }
-    int rc = lp_detect_filter_f32(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream);
+    int rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream, true,
+                           workspace_free_event != nullptr);
     if (rc != LP_OK) return rc;
     if (time_end_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
@@ -495,8 +525,8 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B
     if (e != cudaSuccess) return (int)e;
     e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
     if (e != cudaSuccess) return (int)e;
-    rc = lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
-                                kept_anchor, rescale, do_round, nms_stream);
+    rc = detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                         kept_anchor, rescale, do_round, nms_stream, true);
     if (rc != LP_OK) return rc;
     if (done_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);

@@ -100,6 +100,8 @@ struct NmsParams {
     long long* timing;          // debug only: [B, 16] clock64 stamps per phase, or null
     // fused path only (from_levels != 0): KF left the finished rows of every candidate, pred is null
     int from_levels;
+    int rearm;                  // pipelined entries: zero counts[b] / the tile counter once read, so the
+                                // next filter launch on this workspace needs no memset node
     const float* rec;           // [B, A, 28] by slot
     const unsigned* slot_of;    // [B, A]
 };

@@ -179,6 +179,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     if (tid < 32) words[tid] = 0;
     if (tid == 0) s_nkeep = 0;
     __syncthreads();
+    if (p.rearm && tid == 0) {  // every thread has read counts[b]; the filter kernel of this workspace is done
+        const_cast<int*>(p.counts)[b] = 0;
+        if (b == 0) const_cast<int*>(p.counts)[gridDim.x] = 0;  // the filter kernels' tile counter
+    }
 
     // W owner threads hold one candidate of a window each; the spare threads work as R-1 replicas
     // of the owners (P = R * W threads take part in the order/NMS barriers), the rest wait for the
