@@ -35,7 +35,7 @@ print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk")
 q = t[:, 8:14].double()
 if float(q[:, 5].sum()) > 0:   # library built with LPNMS_NVCC_EXTRA=-DLP_NMS_PROFILE
     n = q[:, 5].clamp(min=1)
-    print(f"  first window, last warp: {n.mean():.1f} chunk steps; per step: header {(q[:, 0] / n).mean():.0f}  iou {(q[:, 1] / n).mean():.0f}  "
-          f"barrier {(q[:, 2] / n).mean():.0f}  fixed point + update {(q[:, 3] / n).mean():.0f}  barrier {(q[:, 4] / n).mean():.0f} clk")
+    print(f"  last warp: {n.mean():.1f} chunk steps, window staging {q[:, 0].mean():.0f} clk in all; per step: test {(q[:, 1] / n).mean():.0f}  "
+          f"barrier {(q[:, 2] / n).mean():.0f}  settle (warp 0; others skip) {(q[:, 3] / n).mean():.0f}  barrier {(q[:, 4] / n).mean():.0f} clk")
 tot = (t[:, 5] - t[:, 0]).double()
 print(f"  total          mean {tot.mean():9.0f} clk   max {tot.max():9.0f} clk   (SM clock ~1.9 GHz -> {tot.max() / 1.9e3:.1f} us)")

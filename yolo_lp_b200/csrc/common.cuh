@@ -65,13 +65,28 @@ __device__ __forceinline__ float box_area(const float4& b) {
 // (double)ovr > thr.  `thr_floor` is the largest float <= thr, for which the float compare
 // ovr > thr_floor is equivalent.  0/0 -> NaN -> not suppressed.
 __device__ __forceinline__ bool iou_exceeds(const float4& a, float area_a, const float4& b, float area_b, float thr_floor) {
-    const float w = fmaxf(0.0f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
-    const float h = fmaxf(0.0f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
-    const float inter = __fmul_rn(w, h);
-    // inter is +0 for disjoint boxes (the common case): 0/u is 0, -0 or NaN, never > thr (thr >= 0),
-    // so the IEEE division -- whose zero-numerator case runs the slow path -- is skipped exactly.
-    if (!(inter > 0.0f)) return false;
-    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    // Disjoint boxes are the common case and K2 is issue-bound: decide them on the signs of the two
+    // extents alone.  inter = max(0, dx) * max(0, dy) is +0 unless both are positive, and 0 / u is
+    // 0, -0 or NaN, never > thr (thr >= 0) -- so this is exactly the reference's result.
+    const float dx = __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x));
+    const float dy = __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y));
+    if (!(dx > 0.0f && dy > 0.0f)) return false;
+    const float inter = __fmul_rn(dx, dy);
+    if (!(inter > 0.0f)) return false;   // the product of two tiny extents may still round to zero
+    const float u = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+    // The IEEE division costs ~25 instructions: decide without it whenever the quotient is clearly off
+    // the threshold.  With tu = RN(thr * u),
+    //   inter > tu * (1 + 1e-6)  =>  inter / u > thr * (1 + 5e-7) > succ(thr)  =>  RN(inter / u) > thr
+    //   inter < tu * (1 - 1e-6)  =>  inter / u < thr * (1 - 5e-7) < pred(thr)  =>  RN(inter / u) < thr
+    // (two roundings of 2^-24 each against a margin of 1e-6; tu well inside the normal range, so the
+    // relative bounds hold).  Only the band in between -- and the degenerate cases u <= 0, u or tu not
+    // finite, denormal-sized products -- take the exact quotient.
+    const float tu = __fmul_rn(thr_floor, u);
+    if (tu > 1e-30f && tu < 3.0e38f) {   // implies thr > 0, u > 0, both finite
+        if (inter > __fmul_rn(tu, 1.000001f)) return true;
+        if (inter < __fmul_rn(tu, 0.999999f)) return false;
+    }
+    const float ovr = __fdiv_rn(inter, u);
     return ovr > thr_floor;
 }
 

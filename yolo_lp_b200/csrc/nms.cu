@@ -15,15 +15,16 @@
 //                         everything, e.g. all scores equal) falls back to a full bitonic sort, in
 //                         shared memory up to 16384 keys and in the global workspace beyond.
 //   NMS     torchvision.ops.nms CPU semantics (call site nms.py:121), bit-exact fp32 IoU, evaluated
-//           lazily and chunk-wise: the ordered list is walked in 512-wide windows (one owner thread
-//           per candidate, the other threads act as replicas that share the IoU work); a window is
-//           first tested against every box kept so far, then resolved 32 candidates (one chunk) at
-//           a time -- every later candidate collects the bitmask S of chunk members that would
-//           suppress it, the chunk's owner warp settles the kept members K in greedy order from those
-//           masks (ballot fixed point) and candidates with S & K die.  Serial depth is the number of
-//           non-empty chunks, IoU work is only done against still-alive members, and everything
-//           stops as soon as max_det rows are kept, which the reference's truncation keep[:max_det]
-//           (nms.py:122-123) makes legal.
+//           lazily: the ordered list is walked one chunk of 32 candidates per step, warp w owning
+//           member w.  Its lanes run over the boxes kept so far (stopping at the first suppressor)
+//           and over the chunk's earlier members; warp 0 then settles the chunk's greedy result from
+//           the 32 "suppressed by an earlier member" masks (ballot fixed point) and appends the kept
+//           boxes.  IoU work is therefore only done for candidates the walk actually reaches --
+//           32 x (kept so far + 16) tests per step -- and everything stops as soon as max_det rows
+//           are kept, which the reference's truncation keep[:max_det] (nms.py:122-123) makes legal.
+//           (The first version resolved 512-wide windows eagerly, every later candidate against every
+//           alive member of the current chunk: 2-3x the IoU tests and three barriers per step;
+//           cfg2 35 -> 28, cfg4 87 -> 60, cfg5 228 -> 110 thousand cycles for this phase.)
 //   gather  kept rows are staged in shared memory, one thread per (row, group) recomputes
 //           nms.py:76-96 (group maxima with first-index argmax), one per (row, coordinate) emits the
 //           xyxy box and the corners, optionally mapped back to source coordinates
@@ -131,13 +132,6 @@ __device__ void rank_sort(unsigned long long* keys, unsigned* acc, unsigned n, u
     bar_active(nthreads);
 }
 
-// bits i of a 32-bit chunk mask with i % R == rep (R replicas share the members of a chunk)
-__device__ __forceinline__ unsigned replica_mask(unsigned R, unsigned rep) {
-    unsigned m = 0;
-    for (unsigned i = rep; i < 32; i += R) m |= 1u << i;
-    return m;
-}
-
 // xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- from the finished
 // row KF stored for it
 template <bool kLevels>
@@ -158,10 +152,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     __shared__ float4 wbox[WIN];              // boxes of the current window
     __shared__ float4 kbox[KEPT_SMEM];        // first KEPT_SMEM kept boxes
     __shared__ int kanchor[KEPT_SMEM];        // and their anchors
-    __shared__ unsigned s_sh[WIN];            // per candidate: members of the current chunk that suppress it
+    __shared__ int wanchor[WIN];              // and their anchors
+    __shared__ unsigned s_alive[32], s_S[32]; // per chunk member: survives the kept list / earlier members that suppress it
     __shared__ unsigned scratch[HIST_BINS];   // score histogram (inclusive scan), lives across segments
     __shared__ unsigned rank_acc[RANK_SORT_MAX];  // rank-sort partial ranks
-    __shared__ unsigned words[32];            // alive bitmask of the window, one word per chunk
     __shared__ unsigned red[32];              // cross-warp reductions
     __shared__ unsigned s_misc[4];            // [0] segment end bin, [1] segment fill counter, [2] kept mask of the chunk
     __shared__ int s_nkeep;
@@ -176,7 +170,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     LP_STAMP(0);
     unsigned N = (unsigned)p.counts[b];
     if (N > p.A) N = p.A;
-    if (tid < 32) words[tid] = 0;
     if (tid == 0) s_nkeep = 0;
     __syncthreads();
     if (p.rearm && tid == 0) {  // every thread has read counts[b]; the filter kernel of this workspace is done
@@ -184,24 +177,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         if (b == 0) const_cast<int*>(p.counts)[gridDim.x] = 0;  // the filter kernels' tile counter
     }
 
-    // W owner threads hold one candidate of a window each; the spare threads work as R-1 replicas
-    // of the owners (P = R * W threads take part in the order/NMS barriers), the rest wait for the
-    // gather.  N >= 512: W = 512, R = 2, P = 1024.
+    // Ordering works with P <= 1024 threads: W slots (N rounded up to a warp, at most 512) times R
+    // replicas that share the rank-sort comparisons.  N > 512: W = 512, R = 2, P = 1024.
     const unsigned W = N >= WIN ? WIN : ((N + 31u) & ~31u);
     const unsigned R = W ? NMS_THREADS / W : 1u, P = R * W;
+    unsigned long long* gkeys = p.keys + (size_t)b * p.key_stride;
+    const unsigned long long* sorted = skeys;
+    bool sorted_global = false, segmented = false;
+    unsigned n_seg = N;         // candidates in the current (sorted) segment
+    unsigned kmin = 0, shift = 0;
 
     if (tid < P && p.max_det > 0) {
-        const unsigned j = tid % W, rep = tid / W;  // candidate slot, replica id (warp-uniform)
-        const unsigned cw = j >> 5;                   // chunk of the slot
-        const bool owner = rep == 0;
-        unsigned long long* gkeys = p.keys + (size_t)b * p.key_stride;
-        int n_keep = 0;
 
         // ------------------------------------------------------------------ ordering mode
-        const unsigned long long* sorted = skeys;
-        bool sorted_global = false, segmented = false;
-        unsigned n_seg = N;         // candidates in the current (sorted) segment
-        unsigned kmin = 0, shift = 0;
         if (N <= RANK_SORT_MAX) {
             for (unsigned i = tid; i < N; i += P) skeys[i] = __ldcg(gkeys + i);
             bar_active(P);
@@ -276,196 +264,175 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         bar_active(P);
         LP_STAMP(2);  // ordered (or histogram ready)
 
-        const unsigned lower = (1u << lane) - 1u;
-        const unsigned my_members = replica_mask(R, rep);
-        const unsigned n_chunks = W >> 5;
-        unsigned consumed = 0;   // candidates of earlier segments
-        unsigned seg_bin0 = 0;   // first histogram bin of the next segment
-        bool first_window = true;
-        while (consumed < N && consumed < (unsigned)p.max_nms && n_keep < p.max_det) {
-            if (segmented) {
-                // ---- next segment: bins [seg_bin0, e] with e the first bin reaching SEG_TARGET keys
-                const unsigned base_cnt = seg_bin0 ? scratch[seg_bin0 - 1] : 0u;
-                if (tid == 0) { s_misc[0] = HIST_BINS - 1; s_misc[1] = 0; }
-                bar_active(P);
-                if (tid >= seg_bin0 && scratch[tid] - base_cnt >= (unsigned)SEG_TARGET) atomicMin(&s_misc[0], tid);
-                bar_active(P);
-                const unsigned e = s_misc[0];
-                n_seg = scratch[e] - base_cnt;
-                for (unsigned i0 = 0; i0 < N; i0 += P) {  // warp-aggregated compaction, order irrelevant
-                    const unsigned i = i0 + tid;
-                    unsigned long long key = 0;
-                    bool take = false;
-                    if (i < N) {
-                        key = __ldcg(gkeys + i);
-                        const unsigned bin = ((unsigned)(key >> 32) - kmin) >> shift;
-                        take = bin >= seg_bin0 && bin <= e;
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, take);
-                    unsigned base = 0;
-                    if (lane == 0 && m) base = atomicAdd(&s_misc[1], (unsigned)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (take) skeys[base + __popc(m & lower)] = key;
-                }
-                bar_active(P);
-                if (n_seg <= (unsigned)RANK_SORT_MAX) {
-                    rank_sort(skeys, rank_acc, n_seg, P);
-                    sorted = skeys + RANK_SORT_MAX;
-                } else {
-                    const unsigned npad = next_pow2(n_seg);
-                    for (unsigned i = n_seg + tid; i < npad; i += P) skeys[i] = ~0ull;
-                    bar_active(P);
-                    bitonic_sort<false>(skeys, npad, P);
-                    sorted = skeys;
-                }
-                seg_bin0 = e + 1;
-            }
-            const unsigned n_use = min(n_seg, (unsigned)p.max_nms - consumed);  // nms.py:115-116
+    }
+    // threads that sat the ordering out (P < 1024 only happens for N <= 512) know where the list is
+    if (N <= RANK_SORT_MAX) sorted = skeys + RANK_SORT_MAX;
+    __syncthreads();
 
-            // -------------------------------------------------------------- windows of the segment
-            for (unsigned w0 = 0; w0 < n_use && n_keep < p.max_det; w0 += W) {
-                unsigned anchor = 0;
-                bool valid = false;
-                if (owner) {
-                    const unsigned pos = w0 + j;
-                    valid = pos < n_use;
-                    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (valid) {
-                        anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
-                        bx = candidate_box<kLevels>(p, pred, b, anchor);  // nms.py:79
-                    }
-                    wbox[j] = bx;
-                    s_sh[j] = 0;
-                }
-                bar_active(P);
-                const float4 box = wbox[j];
-                const float area = box_area(box);
-                if (n_keep > 0) {
-                    // suppression by boxes kept in earlier windows / segments, shared by the replicas
-                    if (w0 + j < n_use) {
-                        bool hit = false;
-                        for (int k = (int)rep; k < n_keep; k += (int)R) {
-                            const float4 kb = k < KEPT_SMEM ? kbox[k] : __ldcg(kept_box + k);
-                            hit |= iou_exceeds(kb, box_area(kb), box, area, p.iou_floor);
-                        }
-                        if (hit) s_sh[j] = 1;
-                    }
-                    bar_active(P);
-                }
-                if (owner) {
-                    const bool alive = valid && s_sh[j] == 0;
-                    if (n_keep > 0) s_sh[j] = 0;
-                    const unsigned word = __ballot_sync(0xffffffffu, alive);
-                    if (lane == 0) words[cw] = word;
-                }
-                bar_active(P);
-                if (first_window) { LP_STAMP(3); first_window = false; }  // first window loaded
-
-                int c = -1;
+    // ---------------------------------------------------------------------- NMS, all 32 warps
+    // The ordered list is walked 32 candidates (one chunk) per step, warp w owning member w:
+    //   test     lanes run over the boxes kept so far (kbox, 16-byte conflict-free LDS) plus the
+    //            chunk's earlier members: `alive` = no kept box suppresses the member, S = mask of
+    //            earlier chunk members that would (if they end up kept);
+    //   settle   warp 0, lane i = member i: K = the greedy result inside the chunk (ballot fixed
+    //            point over the S masks), cut to the room left under max_det; kept members append
+    //            their box / anchor to the kept list.
+    // Two CTA barriers per step; work is only ever done for candidates the walk actually reaches and
+    // stops as soon as max_det rows are kept (nms.py:122-123 makes that legal).  Candidate boxes are
+    // gathered WIN at a time into shared memory.
+    const unsigned warp = tid >> 5;
+    const unsigned lower = (1u << lane) - 1u;
+    const float iou_floor = p.iou_floor;
+    int n_keep = 0;
+    unsigned consumed = 0;   // candidates of earlier segments
+    unsigned seg_bin0 = 0;   // first histogram bin of the next segment
+    bool first_window = true;
 #ifdef LP_NMS_PROFILE
-                long long pf_hdr = 0, pf_iou = 0, pf_b0 = 0, pf_fix = 0, pf_b2 = 0, pf_n = 0, pf_t = clock64();
-#define LP_PF(acc) do { const long long t1_ = clock64(); acc += t1_ - pf_t; pf_t = t1_; } while (0)
+    long long pf_hdr = 0, pf_iou = 0, pf_b0 = 0, pf_fix = 0, pf_b2 = 0, pf_n = 0, pf_t = clock64();
+    // only the last warp reads the clock: 32 warps doing so right after a barrier serialise on CS2R
+#define LP_PF(acc) do { if (warp == 31) { const long long t1_ = clock64(); acc += t1_ - pf_t; pf_t = t1_; } } while (0)
 #else
 #define LP_PF(acc) do { } while (0)
 #endif
-                while (true) {
-                    // next chunk that still has alive members; every warp computes it redundantly
-                    const unsigned wl = ((int)lane > c && lane < n_chunks) ? words[lane] : 0u;
-                    const unsigned nz = __ballot_sync(0xffffffffu, wl != 0);
-                    if (!nz) break;
-                    const bool alive = (words[cw] >> lane) & 1u;
-                    c = __ffs(nz) - 1;
-                    const unsigned A = __shfl_sync(0xffffffffu, wl, c);
-                    LP_PF(pf_hdr);
-                    // S: members of chunk c that suppress this thread's candidate if they are kept;
-                    // every replica looks at its share of the alive members
-                    if ((int)cw >= c && alive) {
-                        const float4* cb = wbox + c * 32;
-                        unsigned S = 0;
-                        // four members per round: independent IoU chains (ILP); the trip count
-                        // depends only on A and the replica, so it is warp-uniform
-                        for (unsigned m = A & my_members; m;) {
-                            int idx[4];
-                            unsigned bit[4];
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                idx[r] = m ? __ffs(m) - 1 : 0;
-                                bit[r] = m & (0u - m);  // lowest set bit, 0 once the share is exhausted
-                                m &= m - 1;
-                            }
-#pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                if (bit[r] == 0) continue;  // share exhausted (warp-uniform)
-                                const float4 kb = cb[idx[r]];
-                                if (iou_exceeds(kb, box_area(kb), box, area, p.iou_floor)) S |= bit[r];
-                            }
+    while (p.max_det > 0 && consumed < N && consumed < (unsigned)p.max_nms && n_keep < p.max_det) {
+        if (segmented) {
+            // ---- next segment: bins [seg_bin0, e] with e the first bin reaching SEG_TARGET keys
+            const unsigned base_cnt = seg_bin0 ? scratch[seg_bin0 - 1] : 0u;
+            if (tid == 0) { s_misc[0] = HIST_BINS - 1; s_misc[1] = 0; }
+            bar_active(P);
+            if (tid >= seg_bin0 && scratch[tid] - base_cnt >= (unsigned)SEG_TARGET) atomicMin(&s_misc[0], tid);
+            bar_active(P);
+            const unsigned e = s_misc[0];
+            n_seg = scratch[e] - base_cnt;
+            for (unsigned i0 = 0; i0 < N; i0 += P) {  // warp-aggregated compaction, order irrelevant
+                const unsigned i = i0 + tid;
+                unsigned long long key = 0;
+                bool take = false;
+                if (i < N) {
+                    key = __ldcg(gkeys + i);
+                    const unsigned bin = ((unsigned)(key >> 32) - kmin) >> shift;
+                    take = bin >= seg_bin0 && bin <= e;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, take);
+                unsigned base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_misc[1], (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (take) skeys[base + __popc(m & lower)] = key;
+            }
+            bar_active(P);
+            if (n_seg <= (unsigned)RANK_SORT_MAX) {
+                rank_sort(skeys, rank_acc, n_seg, P);
+                sorted = skeys + RANK_SORT_MAX;
+            } else {
+                const unsigned npad = next_pow2(n_seg);
+                for (unsigned i = n_seg + tid; i < npad; i += P) skeys[i] = ~0ull;
+                bar_active(P);
+                bitonic_sort<false>(skeys, npad, P);
+                sorted = skeys;
+            }
+            seg_bin0 = e + 1;
+        }
+        const unsigned n_use = min(n_seg, (unsigned)p.max_nms - consumed);  // nms.py:115-116
+
+
+        for (unsigned w0 = 0; w0 < n_use && n_keep < p.max_det; w0 += WIN) {
+            const unsigned n_win = min((unsigned)WIN, n_use - w0);
+            if (tid < n_win) {
+                const unsigned pos = w0 + tid;
+                const unsigned anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
+                wbox[tid] = candidate_box<kLevels>(p, pred, b, anchor);  // nms.py:79
+                wanchor[tid] = (int)anchor;
+            }
+            __syncthreads();
+            if (first_window) { LP_STAMP(3); first_window = false; }  // first window loaded
+            LP_PF(pf_hdr);
+            for (unsigned c0 = 0; c0 < n_win && n_keep < p.max_det; c0 += 32) {
+                // ---- test: warp w <-> member c0 + w
+                const unsigned idx = c0 + warp;
+                if (idx < n_win) {  // warp-uniform
+                    const float4 box = wbox[idx];
+                    const float area = box_area(box);
+                    // kept boxes in shared memory first (all of them unless max_det > KEPT_SMEM), in a loop
+                    // without the global fall-back's address arithmetic; stops at the first suppressor
+                    bool dead = false;
+                    const int n_s = min(n_keep, KEPT_SMEM);
+                    const float4* kb_lane = kbox + lane;
+                    for (int k0 = 0; k0 < n_s && !dead; k0 += 32) {
+                        bool hit = false;
+                        if (k0 + (int)lane < n_s) {
+                            const float4 kb = kb_lane[k0];
+                            hit = iou_exceeds(kb, box_area(kb), box, area, iou_floor);
                         }
-                        if ((int)cw == c) S &= lower;  // only earlier members of the own chunk count
-                        if (S) atomicOr(&s_sh[j], S);
+                        dead = __any_sync(0xffffffffu, hit);
                     }
-                    LP_PF(pf_iou);
-                    bar_active(P);
-                    LP_PF(pf_b0);
-                    // greedy inside the chunk, settled by the chunk's owner warp: K_i = A_i and no kept
-                    // earlier member suppresses i (lane i holds the suppressor mask of member i).  One
-                    // ballot per round; a shuffle loop over the members was measured 2x slower.
-                    if (owner && (int)cw == c) {
-                        const unsigned sc = s_sh[j];
-                        const bool in_a = (A >> lane) & 1u;
-                        unsigned K = A;
-                        while (true) {  // K <- F(K) fixes one more leading member per round; the unique
-                            const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);  // fixed point is
-                            if (K2 == K) break;                                                      // the greedy result
-                            K = K2;
+                    for (int k0 = KEPT_SMEM; k0 < n_keep && !dead; k0 += 32) {
+                        bool hit = false;
+                        if (k0 + (int)lane < n_keep) {
+                            const float4 kb = __ldcg(kept_box + k0 + lane);
+                            hit = iou_exceeds(kb, box_area(kb), box, area, iou_floor);
                         }
-                        const int room = p.max_det - n_keep;
-                        if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
-                        if ((K >> lane) & 1u) {
-                            const int k = n_keep + __popc(K & lower);
-                            if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = (int)anchor; }
-                            else { kept_box[k] = box; kept_anchor[k] = (int)anchor; }
-                        }
-                        if (lane == 0) {
-                            s_misc[2] = K;
-                            words[cw] = 0;  // every member is now kept or suppressed
-                        }
+                        dead = __any_sync(0xffffffffu, hit);
                     }
-                    bar_active(P);
-                    const unsigned K = s_misc[2];
-                    if (owner && (int)cw > c) {
-                        bool still = alive;
-                        if (alive) {
-                            const unsigned S = s_sh[j];
-                            if (S) s_sh[j] = 0;
-                            still = (S & K) == 0;
+                    unsigned S = 0;
+                    if (!dead) {  // earlier members of the chunk (all of them exist: c0 + lane < idx)
+                        bool over = false;
+                        if (lane < warp) {
+                            const float4 mb = wbox[c0 + lane];
+                            over = iou_exceeds(mb, box_area(mb), box, area, iou_floor);
                         }
-                        const unsigned word = __ballot_sync(0xffffffffu, still);
-                        if (lane == 0) words[cw] = word;
+                        S = __ballot_sync(0xffffffffu, over);
                     }
-                    n_keep += __popc(K);
-                    LP_PF(pf_fix);
-                    if (n_keep >= p.max_det) break;
-                    bar_active(P);
-                    LP_PF(pf_b2);
+                    if (lane == 0) { s_alive[warp] = dead ? 0u : 1u; s_S[warp] = S; }
+                } else if (lane == 0) {
+                    s_alive[warp] = 0u;
+                    s_S[warp] = 0u;
+                }
+                LP_PF(pf_iou);
+                __syncthreads();
+                LP_PF(pf_b0);
+                // ---- settle: K_i = alive_i and no kept earlier member suppresses i.  K <- F(K) fixes at
+                // least one more leading member per round; the unique fixed point is the greedy result.
+                if (warp == 0) {
+                    const bool in_a = s_alive[lane] != 0u;
+                    const unsigned sc = s_S[lane];
+                    unsigned K = __ballot_sync(0xffffffffu, in_a);
+                    while (true) {
+                        const unsigned K2 = __ballot_sync(0xffffffffu, in_a && (sc & K) == 0);
+                        if (K2 == K) break;
+                        K = K2;
+                    }
+                    const int room = p.max_det - n_keep;
+                    if (__popc(K) > room) K &= (1u << __fns(K, 0, room + 1)) - 1u;  // first `room` members only
+                    if ((K >> lane) & 1u) {
+                        const int k = n_keep + __popc(K & lower);
+                        const float4 box = wbox[c0 + lane];
+                        const int anchor = wanchor[c0 + lane];
+                        if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = anchor; }
+                        else { kept_box[k] = box; kept_anchor[k] = anchor; }
+                    }
+                    if (lane == 0) s_misc[2] = K;
+                }
+                LP_PF(pf_fix);
+                __syncthreads();
+                n_keep += __popc(s_misc[2]);
+                LP_PF(pf_b2);
 #ifdef LP_NMS_PROFILE
-                    ++pf_n;
+                ++pf_n;
 #endif
-                }
+            }
+        }
+        consumed += n_seg;
+        if (!segmented) break;
+    }
 #ifdef LP_NMS_PROFILE
-                if (w0 == 0 && consumed == 0 && p.timing != nullptr && tid == P - 1) {  // last warp: in every step
-                    long long* q = p.timing + (size_t)b * 16 + 8;
-                    q[0] = pf_hdr; q[1] = pf_iou; q[2] = pf_b0; q[3] = pf_fix; q[4] = pf_b2; q[5] = pf_n;
-                }
+    if (p.timing != nullptr && tid == NMS_THREADS - 1) {  // last warp
+        long long* q = p.timing + (size_t)b * 16 + 8;
+        q[0] = pf_hdr; q[1] = pf_iou; q[2] = pf_b0; q[3] = pf_fix; q[4] = pf_b2; q[5] = pf_n;
+    }
 #endif
 #undef LP_PF
-                bar_active(P);  // kbox / kept_* visible, wbox / words / s_sh free for the next window
-            }
-            consumed += n_seg;
-            if (!segmented) break;
-        }
-        if (tid == 0) s_nkeep = n_keep;
-        LP_STAMP(4);  // NMS done
-    }
+    if (tid == 0) s_nkeep = n_keep;
+    LP_STAMP(4);  // NMS done
     __syncthreads();
 
     // ---------------------------------------------------------------------- gather
@@ -473,7 +440,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     // aligned), then one thread per (row, group) scans its <= 37 class scores in order -- strict
     // '>' keeps the first maximum like torch.max on CPU -- and one thread per (row, coordinate)
     // emits the box / corner columns.
-    const int n_keep = s_nkeep;
+    n_keep = s_nkeep;
     if (tid == 0) p.out_counts[b] = n_keep;
     float* srow = reinterpret_cast<float*>(smem_raw);
     const int cap_rows = (int)(((size_t)p.sort_smem_keys * sizeof(unsigned long long)) / (ROW * 4));
