@@ -547,6 +547,20 @@ def test_degenerate_scores_take_the_full_sort_fallbacks(A):
     _check_against_oracle(pred, 0.25, 0.45, 300, f"degenerate A={A}")
 
 
+@pytest.mark.parametrize("A,levels", [(600, 1), (1000, 1), (3000, 1), (9000, 1), (700, 3), (5000, 7), (8400, 40)])
+def test_tied_scores_take_the_network_sorts_inside_a_segment(A, levels):
+    """`levels` distinct scores only: the histogram bins hold hundreds to thousands of keys, far above
+    the counting sort's 128-key bin limit, so the segments are ordered by the bitonic networks
+    (block_sort up to 1024 keys, the shared-memory bitonic sort beyond) and ties fall back on the
+    anchor index.  One level = a single bin holding everything."""
+    pred = synth.synth_head(1, A, 640, 24, 0, seed=13)
+    g = torch.Generator().manual_seed(5)
+    lv = torch.randint(levels, (A, 1), generator=g).float() / max(levels, 2) * 0.4 + 0.5
+    pred[0, :, 13:] = lv
+    pred[0, :, 0:2] = torch.rand((A, 2), generator=g) * 600.0
+    _check_against_oracle(pred, 0.25, 0.45, 300, f"tied scores A={A} levels={levels}")
+
+
 def test_heavy_suppression_walks_many_segments():
     """Few tight clusters, every anchor a candidate: far fewer than max_det boxes survive, so the
     greedy walk has to consume every score segment (and every window) of the 8400 candidates."""

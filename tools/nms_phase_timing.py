@@ -30,6 +30,9 @@ d = torch.stack([t[:, 2] - t[:, 0], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5
 print(f"cfg{cid}: B={B}  candidates/img={plan.candidate_counts().float().mean().item():.0f}  kept/img={plan.counts.float().mean().item():.0f}")
 for i, n in enumerate(names):
     print(f"  {n:26s} mean {d[:, i].mean():9.0f} clk   max {d[:, i].max():9.0f} clk")
+if int(t[:, 7].sum()) > 0:   # segmented ordering: split "first segment + window"
+    print(f"    first segment: {t[:, 14].double().mean():.0f} keys; compaction {(t[:, 1] - t[:, 2]).double().mean():.0f} clk, "
+          f"sort {(t[:, 7] - t[:, 1]).double().mean():.0f} clk, window staging {(t[:, 3] - t[:, 7]).double().mean():.0f} clk")
 g1 = (t[:, 6] - t[:, 4]).double()
 print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk")
 q = t[:, 8:14].double()

@@ -6,14 +6,18 @@
 //   order   keys (score desc, anchor asc) from K1.  Ascending key order reproduces torchvision's
 //           stable descending sort over the anchor-ordered compaction (nms.py:97,121); more than
 //           max_nms candidates are cut to the first max_nms (nms.py:115-116).
-//             N <= 1024   rank sort in shared memory (rank = number of smaller keys)
-//             N <= 2048   bitonic sort in shared memory
+//             N <= 384    rank sort in shared memory (rank = number of smaller keys)
 //             larger      SEGMENTED: a 1024-bin histogram over the score bits splits the candidates
 //                         into score-ordered segments of >= 512 keys; only the segments the greedy
-//                         walk actually reaches are compacted and sorted (with max_det = 300 that is
-//                         usually the first one or two).  A pathological histogram (one bin holding nearly
-//                         everything, e.g. all scores equal) falls back to a full bitonic sort, in
-//                         shared memory up to 16384 keys and in the global workspace beyond.
+//                         walk actually reaches are ordered (with max_det = 300 that is usually the
+//                         first one or two).  A segment whose bins all hold <= 128 keys -- the normal
+//                         case -- is a counting sort: keys are scattered to their bin's slice and
+//                         ranked inside it (<= 128 comparisons per key); otherwise it is compacted and
+//                         sorted by a bitonic network (block_sort: shuffles + 15 smem exchanges up to
+//                         1024 keys).  A pathological histogram (one bin holding nearly everything,
+//                         e.g. all scores equal) falls back to a full sort, in shared memory up to
+//                         16384 keys and in the global workspace beyond.  The image's keys are cached
+//                         in shared memory (N <= 12288) for the three-plus passes this mode makes.
 //   NMS     torchvision.ops.nms CPU semantics (call site nms.py:121), bit-exact fp32 IoU, evaluated
 //           lazily: the ordered list is walked one chunk of 32 candidates per step, warp w owning
 //           member w.  Its lanes run over the boxes kept so far (stopping at the first suppressor)
@@ -36,10 +40,13 @@ namespace lp {
 constexpr int NMS_THREADS = 1024;
 constexpr int WIN = 512;               // candidates per window
 constexpr int SORT_SMEM_KEYS = 16384;  // 128 KB sort buffer (later the row staging area)
-constexpr int RANK_SORT_MAX = 1024;    // rank sort: input keys [0, n), output keys [RANK_SORT_MAX, RANK_SORT_MAX + n)
-constexpr int DIRECT_SORT_MAX = 2048;  // up to here everything is sorted at once
+constexpr int BLOCK_SORT_MAX = 1024;   // block_sort: input keys [0, n), output keys [BLOCK_SORT_MAX, BLOCK_SORT_MAX + n)
+constexpr int RANK_SORT_N = 384;       // up to here the n^2 rank sort (one pass, three barriers) beats the network
 constexpr int HIST_BINS = 1024;
 constexpr int SEG_TARGET = 512;        // minimum candidates per segment
+constexpr int COUNTING_BIN_MAX = 128;  // a segment whose bins are all this small is ordered by counting sort
+constexpr int COUNTING_SEG_MAX = 2048; // ... if it fits skeys[0, 2048) -> skeys[2048, 4096)
+constexpr int KEY_CACHE_AT = 4 * BLOCK_SORT_MAX;  // segmented mode: the image's keys are cached in skeys[KEY_CACHE_AT, +N)
 constexpr int KEPT_SMEM = 1024;        // kept boxes / anchors cached in shared memory (rest via L2)
 
 __device__ __forceinline__ unsigned next_pow2(unsigned n) { return n <= 1 ? 1u : 1u << (32 - __clz(n - 1)); }
@@ -100,9 +107,9 @@ __device__ __forceinline__ unsigned lt_u64(unsigned long long a, unsigned long l
     return r & 1u;  // 0 - 0 - borrow = 0xffffffff when a < b
 }
 
-// Rank sort of n <= RANK_SORT_MAX distinct keys (they embed the anchor) by the first `nthreads`
+// Rank sort of n <= RANK_SORT_N distinct keys (they embed the anchor) by the first `nthreads`
 // threads: rank = number of smaller keys.  Keys sit in keys[0, n); the sorted list is written to
-// keys[RANK_SORT_MAX, RANK_SORT_MAX + n).  The n^2 comparisons are spread over all threads: slot
+// keys[BLOCK_SORT_MAX, BLOCK_SORT_MAX + n).  The n^2 comparisons are spread over all threads: slot
 // jj of replica rr counts over the rr-th slice of the keys, two per 128-bit shared-memory load, and
 // the partial ranks are summed in `acc`.  Every one of the `nthreads` threads must call this.
 __device__ void rank_sort(unsigned long long* keys, unsigned* acc, unsigned n, unsigned nthreads) {
@@ -128,8 +135,41 @@ __device__ void rank_sort(unsigned long long* keys, unsigned* acc, unsigned n, u
         atomicAdd(&acc[jj], rank);
     }
     bar_active(nthreads);
-    if (work && rr == 0 && jj < n) keys[RANK_SORT_MAX + acc[jj]] = key;
+    if (work && rr == 0 && jj < n) keys[BLOCK_SORT_MAX + acc[jj]] = key;
     bar_active(nthreads);
+}
+
+// Ascending sort of n <= BLOCK_SORT_MAX keys by the whole CTA, one key per thread: keys[0, n) ->
+// keys[BLOCK_SORT_MAX, BLOCK_SORT_MAX + n).  A bitonic network whose exchanges at distance < 32 are
+// warp shuffles (no barrier, no shared memory); only the 15 (of 55) steps at distance >= 32 go
+// through a double-buffered exchange area keys[2 * BLOCK_SORT_MAX, 4 * BLOCK_SORT_MAX) with one
+// barrier each.  (The first version was a rank sort -- n^2 comparisons -- that took 22 thousand
+// cycles for a 534-key segment; this takes about four.)  Every thread of the CTA must call it.
+__device__ void block_sort(unsigned long long* keys, unsigned n) {
+    const unsigned i = threadIdx.x;
+    const unsigned npad = n <= 32 ? 32u : next_pow2(n);
+    const bool active = i < npad;   // warps beyond the padded size only keep the barriers company
+    unsigned long long key = i < n ? keys[i] : ~0ull;  // pads sort to the end
+    unsigned long long* xbuf = keys + 2 * BLOCK_SORT_MAX;
+    unsigned cur = 0;
+    for (unsigned k = 2; k <= npad; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            unsigned long long other = key;
+            if (j >= 32) {
+                if (active) xbuf[cur * BLOCK_SORT_MAX + i] = key;
+                __syncthreads();
+                if (active) other = xbuf[cur * BLOCK_SORT_MAX + (i ^ j)];
+                cur ^= 1u;  // the next exchange writes the other buffer: no second barrier needed
+            } else if (active) {  // warp-uniform: npad is a multiple of 32
+                other = __shfl_xor_sync(0xffffffffu, key, j);
+            }
+            // the lower index of a pair keeps the minimum in an ascending block, the maximum otherwise
+            const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+            key = keep_min ? (other < key ? other : key) : (other > key ? other : key);
+        }
+    }
+    if (i < n) keys[BLOCK_SORT_MAX + i] = key;
+    __syncthreads();
 }
 
 // xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- from the finished
@@ -150,12 +190,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // sort buffer, later row staging
     __shared__ float4 wbox[WIN];              // boxes of the current window
+    __shared__ unsigned rank_acc[RANK_SORT_N]; // rank-sort partial ranks
     __shared__ float4 kbox[KEPT_SMEM];        // first KEPT_SMEM kept boxes
     __shared__ int kanchor[KEPT_SMEM];        // and their anchors
     __shared__ int wanchor[WIN];              // and their anchors
     __shared__ unsigned s_alive[32], s_S[32]; // per chunk member: survives the kept list / earlier members that suppress it
     __shared__ unsigned scratch[HIST_BINS];   // score histogram (inclusive scan), lives across segments
-    __shared__ unsigned rank_acc[RANK_SORT_MAX];  // rank-sort partial ranks
+    __shared__ unsigned fill[HIST_BINS];      // counting sort: keys placed so far per bin
     __shared__ unsigned red[32];              // cross-warp reductions
     __shared__ unsigned s_misc[4];            // [0] segment end bin, [1] segment fill counter, [2] kept mask of the chunk
     __shared__ int s_nkeep;
@@ -177,30 +218,37 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         if (b == 0) const_cast<int*>(p.counts)[gridDim.x] = 0;  // the filter kernels' tile counter
     }
 
-    // Ordering works with P <= 1024 threads: W slots (N rounded up to a warp, at most 512) times R
-    // replicas that share the rank-sort comparisons.  N > 512: W = 512, R = 2, P = 1024.
-    const unsigned W = N >= WIN ? WIN : ((N + 31u) & ~31u);
-    const unsigned R = W ? NMS_THREADS / W : 1u, P = R * W;
+    constexpr unsigned P = NMS_THREADS;   // every phase runs on the whole CTA
     unsigned long long* gkeys = p.keys + (size_t)b * p.key_stride;
     const unsigned long long* sorted = skeys;
     bool sorted_global = false, segmented = false;
     unsigned n_seg = N;         // candidates in the current (sorted) segment
     unsigned kmin = 0, shift = 0;
+    // Segmented mode passes over all keys three times or more (range, histogram, one compaction per
+    // segment): cache them behind the sort area when they fit (N <= 12288) instead of going to L2.
+    bool key_cache = N > (unsigned)RANK_SORT_N && N + KEY_CACHE_AT <= (unsigned)p.sort_smem_keys;
+    unsigned long long* ckeys = skeys + KEY_CACHE_AT;
 
-    if (tid < P && p.max_det > 0) {
+    if (N > 0 && p.max_det > 0) {
 
         // ------------------------------------------------------------------ ordering mode
-        if (N <= RANK_SORT_MAX) {
+        if (N <= (unsigned)RANK_SORT_N) {
             for (unsigned i = tid; i < N; i += P) skeys[i] = __ldcg(gkeys + i);
             bar_active(P);
-            rank_sort(skeys, rank_acc, N, P);
-            sorted = skeys + RANK_SORT_MAX;
+            // W slots (N rounded up to a warp) times R replicas share the comparisons
+            const unsigned W = (N + 31u) & ~31u, Pr = (NMS_THREADS / W) * W;
+            if (tid < Pr) rank_sort(skeys, rank_acc, N, Pr);
+            __syncthreads();
+            sorted = skeys + BLOCK_SORT_MAX;
         } else {
-            if (N > DIRECT_SORT_MAX) {
+            {
                 // ---- histogram of the score bits (upper key word); P == 1024 == HIST_BINS here
                 unsigned lo = 0xffffffffu, hi = 0;
+#pragma unroll 4
                 for (unsigned i = tid; i < N; i += P) {
-                    const unsigned k = (unsigned)(__ldcg(gkeys + i) >> 32);
+                    const unsigned long long key = __ldcg(gkeys + i);
+                    if (key_cache) ckeys[i] = key;
+                    const unsigned k = (unsigned)(key >> 32);
                     lo = min(lo, k);
                     hi = max(hi, k);
                 }
@@ -216,7 +264,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 scratch[tid] = 0;
                 bar_active(P);
                 for (unsigned i = tid; i < N; i += P)
-                    atomicAdd(&scratch[((unsigned)(__ldcg(gkeys + i) >> 32) - kmin) >> shift], 1u);
+                    atomicAdd(&scratch[((unsigned)((key_cache ? ckeys[i] : __ldcg(gkeys + i)) >> 32) - kmin) >> shift], 1u);
                 bar_active(P);
                 // inclusive scan over the 1024 bins (one per thread)
                 const unsigned cnt = scratch[tid];
@@ -244,11 +292,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 const unsigned biggest = __reduce_max_sync(0xffffffffu, red[lane]);
                 // a segment is the shortest run of bins reaching SEG_TARGET keys: it fits the sort
                 // buffer unless a single bin is huge
-                segmented = biggest <= (unsigned)(p.sort_smem_keys - SEG_TARGET - RANK_SORT_MAX);
+                segmented = biggest <= (unsigned)(p.sort_smem_keys - SEG_TARGET - BLOCK_SORT_MAX);
+                // a segment longer than the sort area in front of the cache would overwrite it
+                key_cache = key_cache && segmented && biggest + SEG_TARGET <= (unsigned)KEY_CACHE_AT;
             }
             if (!segmented) {
                 const unsigned npad = next_pow2(N);
-                if (npad <= (unsigned)p.sort_smem_keys) {
+                if (N <= (unsigned)BLOCK_SORT_MAX) {
+                    for (unsigned i = tid; i < N; i += P) skeys[i] = __ldcg(gkeys + i);
+                    bar_active(P);
+                    block_sort(skeys, N);
+                    sorted = skeys + BLOCK_SORT_MAX;
+                } else if (npad <= (unsigned)p.sort_smem_keys) {
                     for (unsigned i = tid; i < npad; i += P) skeys[i] = i < N ? __ldcg(gkeys + i) : ~0ull;
                     bar_active(P);
                     bitonic_sort<false>(skeys, npad, P);
@@ -265,8 +320,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         LP_STAMP(2);  // ordered (or histogram ready)
 
     }
-    // threads that sat the ordering out (P < 1024 only happens for N <= 512) know where the list is
-    if (N <= RANK_SORT_MAX) sorted = skeys + RANK_SORT_MAX;
     __syncthreads();
 
     // ---------------------------------------------------------------------- NMS, all 32 warps
@@ -304,25 +357,55 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
             bar_active(P);
             const unsigned e = s_misc[0];
             n_seg = scratch[e] - base_cnt;
-            for (unsigned i0 = 0; i0 < N; i0 += P) {  // warp-aggregated compaction, order irrelevant
+            // largest bin of the segment
+            if (tid == 0) s_misc[3] = 0;
+            fill[tid] = 0;
+            bar_active(P);
+            if (tid >= seg_bin0 && tid <= e) atomicMax(&s_misc[3], scratch[tid] - (tid ? scratch[tid - 1] : 0u));
+            bar_active(P);
+            const bool counting = s_misc[3] <= (unsigned)COUNTING_BIN_MAX && n_seg <= (unsigned)COUNTING_SEG_MAX;
+            // Compaction.  Counting mode: the histogram already orders the keys by bin, so a key goes
+            // straight to its bin's slice (slot within the bin from an atomic counter, arbitrary);
+            // otherwise warp-aggregated appends in arbitrary order.
+            for (unsigned i0 = 0; i0 < N; i0 += P) {
                 const unsigned i = i0 + tid;
                 unsigned long long key = 0;
                 bool take = false;
+                unsigned bin = 0;
                 if (i < N) {
-                    key = __ldcg(gkeys + i);
-                    const unsigned bin = ((unsigned)(key >> 32) - kmin) >> shift;
+                    key = key_cache ? ckeys[i] : __ldcg(gkeys + i);
+                    bin = ((unsigned)(key >> 32) - kmin) >> shift;
                     take = bin >= seg_bin0 && bin <= e;
                 }
-                const unsigned m = __ballot_sync(0xffffffffu, take);
-                unsigned base = 0;
-                if (lane == 0 && m) base = atomicAdd(&s_misc[1], (unsigned)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (take) skeys[base + __popc(m & lower)] = key;
+                if (counting) {
+                    if (take) skeys[(bin ? scratch[bin - 1] : 0u) - base_cnt + atomicAdd(&fill[bin], 1u)] = key;
+                } else {
+                    const unsigned m = __ballot_sync(0xffffffffu, take);
+                    unsigned base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&s_misc[1], (unsigned)__popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (take) skeys[base + __popc(m & lower)] = key;
+                }
             }
             bar_active(P);
-            if (n_seg <= (unsigned)RANK_SORT_MAX) {
-                rank_sort(skeys, rank_acc, n_seg, P);
-                sorted = skeys + RANK_SORT_MAX;
+            if (consumed == 0) LP_STAMP(1);  // first segment compacted
+            if (counting) {
+                // rank inside the bin's slice: at most COUNTING_BIN_MAX comparisons per key instead of a
+                // sorting network over the whole segment (which took 15-20 thousand cycles for ~500 keys)
+                unsigned long long* out = skeys + COUNTING_SEG_MAX;
+                for (unsigned q = tid; q < n_seg; q += P) {
+                    const unsigned long long key = skeys[q];
+                    const unsigned bin = ((unsigned)(key >> 32) - kmin) >> shift;
+                    const unsigned s0 = (bin ? scratch[bin - 1] : 0u) - base_cnt, s1 = scratch[bin] - base_cnt;
+                    unsigned rank = 0;
+                    for (unsigned r = s0; r < s1; ++r) rank += lt_u64(skeys[r], key);
+                    out[s0 + rank] = key;
+                }
+                bar_active(P);
+                sorted = out;
+            } else if (n_seg <= (unsigned)BLOCK_SORT_MAX) {
+                block_sort(skeys, n_seg);
+                sorted = skeys + BLOCK_SORT_MAX;
             } else {
                 const unsigned npad = next_pow2(n_seg);
                 for (unsigned i = n_seg + tid; i < npad; i += P) skeys[i] = ~0ull;
@@ -331,6 +414,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 sorted = skeys;
             }
             seg_bin0 = e + 1;
+            if (consumed == 0) { LP_STAMP(7); if (p.timing != nullptr && tid == 0) p.timing[(size_t)b * 16 + 14] = n_seg; }
         }
         const unsigned n_use = min(n_seg, (unsigned)p.max_nms - consumed);  // nms.py:115-116
 
