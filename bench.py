@@ -206,7 +206,7 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     (raw level tensors -> [B,A,290]) and the fused path (raw level tensors -> detections).  Synthetic
     level tensors generated on the device; CUDA events; informational (not part of `value`)."""
     import torch
-    from yolo_lp_b200 import synth
+    from yolo_lp_b200 import _abi, synth
     from yolo_lp_b200.head import DecodePlan, PostprocessPlan, PostprocessPipeline
     img = cfg["img"]
     levels = synth.synth_levels(B, img, img, dev, seed=cfg["seed"])
@@ -227,7 +227,14 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     dec = DecodePlan(levels, (8, 16, 32))
     t_dec = timed(dec.run)
     plans = [PostprocessPlan(levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
-    t_kf = timed(lambda: plans[0].run_filter(conf))
+    # KF alone, on the CTA count the serial entry uses (#SMs - #SMs/6); the stage entry on its own
+    # would leave one SM per image free for an overlapping K2, which is what the pipelined leg measures
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    _abi.call("lp_tune", 0, sms - min(B, sms // 6))
+    try:
+        t_kf = timed(lambda: plans[0].run_filter(conf))
+    finally:
+        _abi.call("lp_tune", 0, 0)
     t_serial = timed(lambda: plans[0].run(conf, iou))
     pipe = PostprocessPipeline(plans)
 
