@@ -34,7 +34,7 @@ if int(t[:, 7].sum()) > 0:   # segmented ordering: split "first segment + window
     print(f"    first segment: {t[:, 14].double().mean():.0f} keys; compaction {(t[:, 1] - t[:, 2]).double().mean():.0f} clk, "
           f"sort {(t[:, 7] - t[:, 1]).double().mean():.0f} clk, window staging {(t[:, 3] - t[:, 7]).double().mean():.0f} clk")
 g1 = (t[:, 6] - t[:, 4]).double()
-print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk")
+print(f"  gather: first batch of rows staged after {g1.mean():.0f} clk, its groups re-scored after another {(t[:, 15] - t[:, 6]).double().mean():.0f} clk")
 q = t[:, 8:14].double()
 if float(q[:, 5].sum()) > 0:   # library built with LPNMS_NVCC_EXTRA=-DLP_NMS_PROFILE
     n = q[:, 5].clamp(min=1)

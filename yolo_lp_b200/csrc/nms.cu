@@ -89,6 +89,9 @@ __device__ void bitonic_sort(unsigned long long* keys, unsigned n, unsigned nthr
 __device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
@@ -171,6 +174,8 @@ __device__ void block_sort(unsigned long long* keys, unsigned n) {
     if (i < n) keys[BLOCK_SORT_MAX + i] = key;
     __syncthreads();
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- from the finished
 // row KF stored for it
@@ -493,6 +498,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                         const int anchor = wanchor[c0 + lane];
                         if (k < KEPT_SMEM) { kbox[k] = box; kanchor[k] = anchor; }
                         else { kept_box[k] = box; kept_anchor[k] = anchor; }
+                        // the gather will want this row: start pulling it into L2 now (K1 streamed the
+                        // head tensor with an evict-first policy, so it is most likely back in HBM)
+                        if (!kLevels) {
+                            const char* row = reinterpret_cast<const char*>(pred + (size_t)anchor * ROW);
+#pragma unroll
+                            for (int o = 0; o < ROW * 4 + 127; o += 128) prefetch_l2(row + o);
+                        }
                     }
                     if (lane == 0) s_misc[2] = K;
                 }
@@ -526,8 +538,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     // emits the box / corner columns.
     n_keep = s_nkeep;
     if (tid == 0) p.out_counts[b] = n_keep;
-    float* srow = reinterpret_cast<float*>(smem_raw);
-    const int cap_rows = (int)(((size_t)p.sort_smem_keys * sizeof(unsigned long long)) / (ROW * 4));
+    // Staged rows: pitch 1168 B (16-byte multiple); a row starts 8 bytes into its slot when its
+    // index in the head tensor (b * A + anchor) is odd, so that source (row index * 1160 B from a
+    // 16-byte aligned base: 16-byte aligned only for even rows) and destination agree mod 16 and all
+    // but 8 of the 1160 bytes move as 16-byte cp.async copies.
+    constexpr int SROW_BYTES = 1168;
+    unsigned char* sbytes = smem_raw;
+    const int cap_rows = (int)(((size_t)p.sort_smem_keys * sizeof(unsigned long long)) / SROW_BYTES);
+    const int img_parity = (int)(((size_t)b * p.A) & 1);
+#define LP_SROW(r, anchor) reinterpret_cast<const float*>(sbytes + (size_t)(r) * SROW_BYTES + 8 * (((anchor) + img_parity) & 1))
     const bool do_rescale = p.rescale != nullptr;
     float pad_x = 0.f, pad_y = 0.f, ratio = 1.f, w0f = 0.f, h0f = 0.f;
     if (do_rescale) {
@@ -537,11 +556,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     for (int base = 0; base < n_keep; base += cap_rows) {
         const int nb = min(cap_rows, n_keep - base);
         if (!kLevels) {
-            for (int i = tid; i < nb * (ROW / 2); i += NMS_THREADS) {
-                const int r = i / (ROW / 2), q = i - r * (ROW / 2);
+            for (int r = (int)(tid >> 5); r < nb; r += NMS_THREADS / 32) {  // one warp per row
                 const int k = base + r;
                 const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
-                cp_async_8(srow + r * ROW + 2 * q, pred + (size_t)anchor * ROW + 2 * q);
+                const int odd = (anchor + img_parity) & 1;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(pred + (size_t)anchor * ROW);
+                unsigned char* dst = sbytes + (size_t)r * SROW_BYTES + 8 * odd;
+                // 72 16-byte chunks from the first 16-byte boundary of the row, 8 bytes before (odd) or after (even)
+                for (int c = (int)lane; c < 72; c += 32) cp_async_16(dst + 8 * odd + 16 * c, src + 8 * odd + 16 * c);
+                if (lane == 0) cp_async_8(dst + (odd ? 0 : 1152), src + (odd ? 0 : 1152));
             }
             cp_async_wait_all();
             __syncthreads();
@@ -563,19 +586,32 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         if (base == 0) LP_STAMP(6);  // rows staged
         for (int t = tid; t < nb * NGROUP; t += NMS_THREADS) {
             const int r = t >> 3, g = t & 7;
-            const float* row = srow + r * ROW;
+            const int ka = base + r < KEPT_SMEM ? kanchor[base + r] : kept_anchor[base + r];
+            const float* row = LP_SROW(r, ka);
             const float obj = row[4];
             const int s = group_begin(g), e = group_begin(g + 1);
             float best = __fmul_rn(row[s], obj);  // nms.py:76
             int bi = 0;
-            for (int i = s + 1; i < e; ++i) {
-                const float x = __fmul_rn(row[i], obj);
-                if (x > best) { best = x; bi = i - s; }
+            // The SM is issue-bound here (32 warps, ~280 element visits each): keep the visit short.
+            // Columns past the group's end are replaced by the group's first value -- never '>' the
+            // running maximum -- so the unrolled body needs no bounds predicate; the maximum itself is
+            // an FMNMX and only the index hangs on the compare.  (x > best with best = max so far is
+            // exactly torch.max's first-occurrence rule; NaN scores are outside the head's range.)
+            const float first = best;
+            for (int i0 = s + 1; i0 < e; i0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u;
+                    const float v = i < e ? __fmul_rn(row[i], obj) : first;
+                    bi = v > best ? i - s : bi;
+                    best = fmaxf(best, v);
+                }
             }
             float* dst = p.out + ((size_t)b * p.max_det + base + r) * OUTW;
             dst[12 + g] = best;
             dst[20 + g] = (float)bi;
         }
+        if (base == 0) LP_STAMP(15);  // first batch: groups re-scored
         for (int t = tid; t < nb * 12; t += NMS_THREADS) {
             const int r = t / 12, c = t - r * 12;
             const int k = base + r;
@@ -584,7 +620,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 const float4 bx = k < KEPT_SMEM ? kbox[k] : kept_box[k];
                 val = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : bx.w;
             } else {
-                val = srow[r * ROW + c + 1];  // corners: columns 5..12 -> output 4..11 (nms.py:94)
+                const int ka = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+                val = LP_SROW(r, ka)[c + 1];  // corners: columns 5..12 -> output 4..11 (nms.py:94)
             }
             if (do_rescale)
                 val = (c & 1) ? rescale_coord(val, pad_y, ratio, h0f, p.do_round) : rescale_coord(val, pad_x, ratio, w0f, p.do_round);
@@ -598,6 +635,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         __syncthreads();
     }
     LP_STAMP(5);  // gather done
+#undef LP_SROW
 #undef LP_STAMP
 }
 
