@@ -112,12 +112,15 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
                                void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                const float* rescale, int do_round, lp_stream_t stream);
 
-/* Tuning (process-global, not thread-safe): key 0 = upper bound on the CTAs of K1 / KF (0 = default
- * heuristic); key 1 = 0 forces the cp.async load path of the decode kernel instead of TMA boxes. */
+/* Tuning (process-global, not thread-safe): key 0 = the CTA count of K1 / KF (0 = default
+ * heuristic); key 1 = 0 forces the cp.async / register-resident kernels of the decode and fused
+ * paths instead of their TMA variants (same results; 1 = default, TMA when the shapes allow). */
 LP_API int lp_tune(int key, int value);
 
-/* Debug only (process-global, not thread-safe): device buffer [B,8] of int64 that K2 fills with
- * clock64() stamps at its phase boundaries; NULL switches it off. */
+/* Debug only (process-global, not thread-safe): device buffer [B,16] of int64 that K2 fills with
+ * clock64() stamps at its phase boundaries (tools/nms_phase_timing.py; the decode / fused kernels of
+ * -DLP_DEC_PROFILE / -DLP_KF_PROFILE builds write their per-role cycle sums to it too); NULL
+ * switches it off. */
 LP_API int lp_debug_nms_timing(long long* buf);
 
 /*
