@@ -5,40 +5,52 @@
 // loads, its compare/select chains and the epilogue's global round trips (slot atomics, box / corner
 // reads of the survivors) all sit in one instruction stream.  Here they are three concurrent roles of
 // one persistent CTA per SM, over tiles of 32 positions ([277 class channels][32] = 35,456 B) in a
-// six-deep shared-memory ring:
-//   warps 14-15, lane 0  producers (tiles alternate between them): eight 3-D TMA box loads per tile
+// five-deep shared-memory ring:
+//   warps 22-23, lane 0  producers (tiles alternate between them): eight 3-D TMA box loads per tile
 //                        (UTMALDG.3D, one per class tensor: all its channels x 32 positions of image
 //                        b), completion on the slot's `full` mbarrier, reuse gated by `empty`.  A
-//                        thread needs ~150 cycles per UTMALDG, hence two issuers;
-//   warps 0-7            scanners, warp g owns class group g: lanes along positions (conflict-free
-//                        LDS), running maximum as an FMNMX chain with the first-index / runner-up
-//                        selects hanging off it, two chains per group; one sigmoid of the maximum
-//                        (fused.cu explains why that is exact); leaves score, argmax and tie flag per
-//                        position in a small exchange buffer and bar.arrive's (non-blocking) on the
-//                        tile's named barrier -- scanners only ever wait for data;
-//   warps 8-13           finishers, one per ring slot: bar.sync on the slot's barrier, pull the eight
-//                        groups' results into registers, release the slot, then finish_tile
-//                        (threshold, slot claim, key, the survivors' finished rows): its ~3000 cycles
-//                        of global latency are off everybody else's critical path.  (One finisher
-//                        per SLOT, not a free rotation: with four finishers over six slots a fast
-//                        finisher's bar.sync completed a barrier whose 256 scanner arrivals belonged
-//                        to the slot's previous tile, still waiting for its own slow finisher.)
+//                        thread needs ~100 cycles per UTMALDG, hence two issuers;
+//   warps 0-15           scanners, warp w owns half (w & 1) of class group w >> 1: lanes along
+//                        positions (conflict-free LDS), running maximum as an FMNMX chain with the
+//                        first-index / runner-up selects hanging off it, two interleaved chains;
+//                        leaves (maximum logit, its first index, runner-up before it) per position
+//                        in a small exchange buffer and bar.arrive's (non-blocking) on the slot's
+//                        named barrier -- scanners only ever wait for data.  (Eight scanners, one
+//                        whole group each, needed ~1100 cycles per tile -- a dependent-issue-bound
+//                        instruction stream -- against a ~1300-cycle HBM budget: too close.)
+//   warps 16-21          finishers, tile t belongs to finisher t % 6: wait until the slot's previous
+//                        tile has been taken over (its `empty` phase), bar.sync on the slot's barrier,
+//                        merge the two halves of every group, release the slot, one sigmoid of the
+//                        maximum per group (fused.cu explains why that is exact) plus one for the tie
+//                        test, then finish_tile (threshold, slot claim, key, the survivors' finished
+//                        rows): its global round trips (~2000 cycles) are off everybody else's path.
+//                        (The ordering on `empty` matters: with a free rotation a fast finisher's
+//                        bar.sync completed on the scanner arrivals of the slot's PREVIOUS tile, whose
+//                        own finisher was slow -- seen only on a cold workspace.)
 // Tiles are assigned statically (tile = blockIdx.x + it * gridDim.x): every tile costs the same here.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
 #include "fused_tile.cuh"
 
 namespace lp {
 
-constexpr int KT_RING = 6;
-constexpr int KT_SCANNERS = NGROUP;                  // warps 0..7
-constexpr int KT_FINISHERS = 12;                     // warps 8..19: tile t belongs to finisher t % 12
-constexpr int KT_PRODUCERS = 2;                      // warps 20..21
+constexpr int KT_RING = 5;
+constexpr int KT_SCANNERS = 2 * NGROUP;              // warps 0..15: warp w scans half (w & 1) of group w >> 1
+constexpr int KT_FINISHERS = 6;                      // warps 16..21: tile t belongs to finisher t % 6
+constexpr int KT_PRODUCERS = 2;                      // warps 22..23
 constexpr int KT_THREADS = (KT_SCANNERS + KT_FINISHERS + KT_PRODUCERS) * 32;
 constexpr int KT_STAGE_FLOATS = (ROW - 13) * DEC_TILE;   // class planes only
-constexpr int KT_PART_WORDS = NGROUP * DEC_TILE;         // per ring slot: one word per group and position
-constexpr int KT_SMEM = KT_RING * (KT_STAGE_FLOATS + 2 * KT_PART_WORDS) * 4 + 2 * KT_RING * 8;
+constexpr int KT_PART_WORDS = KT_SCANNERS * DEC_TILE;    // per ring slot: one word per scanner and position
+constexpr int KT_SMEM = KT_RING * (KT_STAGE_FLOATS + 3 * KT_PART_WORDS) * 4 + 2 * KT_RING * 8;
 
-// Named barrier of ring slot s (1..6): the eight scanner warps arrive, the tile's finisher warp waits.
+// Named barrier of ring slot s (1..5): the sixteen scanner warps arrive, the tile's finisher warp waits.
+// (best, arg, before) of a range, followed by the same of a LATER range of the same group
+__device__ __forceinline__ void merge_later(float& best, int& arg, float& before, float b1, int a1, float p1) {
+    const bool later = b1 > best;
+    before = later ? fmaxf(best, p1) : before;
+    arg = later ? a1 : arg;
+    best = fmaxf(best, b1);
+}
+
 __device__ __forceinline__ void slot_arrive(int s) {
     asm volatile("bar.arrive %0, %1;" ::"r"(1 + s), "n"((KT_SCANNERS + 1) * 32) : "memory");
 }
@@ -46,33 +58,34 @@ __device__ __forceinline__ void slot_wait(int s) {
     asm volatile("bar.sync %0, %1;" ::"r"(1 + s), "n"((KT_SCANNERS + 1) * 32) : "memory");
 }
 
-// One group of one anchor from the stage: maximum logit, its FIRST index, and the largest logit that
-// precedes that index (see fused.cu).  Four independent chains over consecutive quarters of the
-// channels, interleaved step by step (a warp issues in order: a single chain leaves it stalled on
-// every compare -> select dependency), then folded left to right: a later quarter wins only with a
-// strictly larger maximum, and then everything in the earlier quarters precedes its index.
-// Within a chain the running maximum is an FMNMX; the compare that drives the selects hangs off it.
-template <int WIDTH>
-__device__ __forceinline__ void group_scan_smem(const float* col0, float& best, int& arg, float& before) {
-    constexpr int NC = 4;
-    constexpr int Q = (WIDTH + NC - 1) / NC;   // chain k covers [k*Q, min((k+1)*Q, WIDTH))
+// Channels [C0, C1) of one group of one anchor from the stage: maximum logit, its FIRST index (within
+// the group), and the largest logit of the range that precedes that index (see fused.cu).  NC
+// independent chains over consecutive sub-ranges, interleaved step by step (a warp issues in order: a
+// single chain leaves it stalled on every compare -> select dependency), then folded left to right: a
+// later sub-range wins only with a strictly larger maximum, and then everything in the earlier ones
+// precedes its index.  Within a chain the running maximum is an FMNMX; the compare that drives the
+// selects hangs off it.
+template <int C0, int C1>
+__device__ __forceinline__ void range_scan_smem(const float* col0, float& best, int& arg, float& before) {
+    constexpr int NC = 2, WIDTH = C1 - C0;
+    constexpr int Q = (WIDTH + NC - 1) / NC;   // chain k covers [C0 + k*Q, min(C0 + (k+1)*Q, C1))
     float bm[NC], pm[NC];
     int am[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        bm[k] = col0[k * Q * DEC_TILE];
+        bm[k] = col0[(C0 + k * Q) * DEC_TILE];
         pm[k] = -INFINITY;
-        am[k] = k * Q;
+        am[k] = C0 + k * Q;
     }
 #pragma unroll
     for (int c = 1; c < Q; ++c) {
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             if (k * Q + c < WIDTH) {
-                const float v = col0[(k * Q + c) * DEC_TILE];
+                const float v = col0[(C0 + k * Q + c) * DEC_TILE];
                 const bool up = v > bm[k];   // strict: the first occurrence of the maximum wins (torch.max)
                 pm[k] = up ? bm[k] : pm[k];
-                am[k] = up ? k * Q + c : am[k];
+                am[k] = up ? C0 + k * Q + c : am[k];
                 bm[k] = fmaxf(bm[k], v);
             }
         }
@@ -81,12 +94,13 @@ __device__ __forceinline__ void group_scan_smem(const float* col0, float& best, 
     arg = am[0];
     before = pm[0];
 #pragma unroll
-    for (int k = 1; k < NC; ++k) {
-        const bool later = bm[k] > best;
-        before = later ? fmaxf(best, pm[k]) : before;
-        arg = later ? am[k] : arg;
-        best = fmaxf(best, bm[k]);
-    }
+    for (int k = 1; k < NC; ++k) merge_later(best, arg, before, bm[k], am[k], pm[k]);
+}
+template <int WIDTH>
+__device__ __forceinline__ void half_scan_smem(const float* col0, int half, float& best, int& arg, float& before) {
+    constexpr int H = WIDTH / 2;
+    if (half == 0) range_scan_smem<0, H>(col0, best, arg, before);
+    else range_scan_smem<H, WIDTH>(col0, best, arg, before);
 }
 
 __device__ __forceinline__ void locate(const LevelsFilterParams& p, int tile, int& b, int& l, int& p0) {
@@ -102,7 +116,7 @@ __device__ __forceinline__ void locate(const LevelsFilterParams& p, int tile, in
 #ifdef LP_KF_PROFILE
 #define LP_PF_DECL long long pf[4] = {0, 0, 0, 0}, pf_t = clock64()
 #define LP_PF(k) do { const long long t1_ = clock64(); pf[k] += t1_ - pf_t; pf_t = t1_; } while (0)
-#define LP_PF_OUT() do { if (p.timing != nullptr && lane == 0) for (int k = 0; k < 4; ++k) p.timing[(blockIdx.x * 22 + warp) * 4 + k] = pf[k]; } while (0)
+#define LP_PF_OUT() do { if (p.timing != nullptr && lane == 0) for (int k = 0; k < 4; ++k) p.timing[(blockIdx.x * 24 + warp) * 4 + k] = pf[k]; } while (0)
 #else
 #define LP_PF_DECL do { } while (0)
 #define LP_PF(k) do { } while (0)
@@ -113,8 +127,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
                                                                             const __grid_constant__ DecodeMaps maps) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* stage0 = reinterpret_cast<float*>(smem);
-    float* part_c = stage0 + KT_RING * KT_STAGE_FLOATS;                              // [ring][group][position] score
-    unsigned* part_a = reinterpret_cast<unsigned*>(part_c + KT_RING * KT_PART_WORDS); // argmax | tie << 8
+    float* part_b = stage0 + KT_RING * KT_STAGE_FLOATS;                          // [ring][scanner][position] maximum logit
+    float* part_p = part_b + KT_RING * KT_PART_WORDS;                            // ... largest logit before its index
+    int* part_a = reinterpret_cast<int*>(part_p + KT_RING * KT_PART_WORDS);      // ... its first index in the group
     uint64_t* full = reinterpret_cast<uint64_t*>(part_a + KT_RING * KT_PART_WORDS);
     uint64_t* empty = full + KT_RING;
 
@@ -157,31 +172,43 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             const DecodeLevel& lv = p.lv[l];
             LP_PF(0);
             // Not before the slot's previous tile has been taken over by ITS finisher: a bar.sync issued
-            // earlier would complete on the 256 scanner arrivals that belong to that tile.
+            // earlier would complete on the 512 scanner arrivals that belong to that tile.
             if (it >= KT_RING) {
                 if (lane == 0) mbar_wait_relaxed(&empty[s], (it / KT_RING - 1) & 1);
                 __syncwarp();
             }
             slot_wait(s);
-            LP_PF(1);               // all eight groups of tile `it` are in the exchange buffer
+            LP_PF(1);               // all sixteen half-group results of tile `it` are in the exchange buffer
             float c[NGROUP];
             unsigned long long args = 0;
             unsigned ties = 0;
+            float best[NGROUP], before[NGROUP];
 #pragma unroll
-            for (int g = 0; g < NGROUP; ++g) {
-                c[g] = part_c[(s * NGROUP + g) * DEC_TILE + lane];
-                const unsigned a = part_a[(s * NGROUP + g) * DEC_TILE + lane];
-                args |= (unsigned long long)(a & 63u) << (6 * g);
-                ties |= (a >> 8) << g;
+            for (int g = 0; g < NGROUP; ++g) {   // the two halves of a group, merged with first-index semantics
+                const int q = (s * KT_SCANNERS + 2 * g) * DEC_TILE + lane;
+                best[g] = part_b[q];
+                before[g] = part_p[q];
+                int arg = part_a[q];
+                merge_later(best[g], arg, before[g], part_b[q + DEC_TILE], part_a[q + DEC_TILE], part_p[q + DEC_TILE]);
+                args |= (unsigned long long)arg << (6 * g);
             }
             __syncwarp();               // every lane has its copy: the slot (stage + exchange) may be refilled
             if (lane == 0) mbar_arrive(&empty[s]);
+            //   score: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
+            //   tie:   arg is the first index of the maximum LOGIT; the reference takes the first index of
+            //          the maximum SIGMOID, which is earlier iff a smaller logit before it rounds to the
+            //          same value -- checked exactly with one more sigmoid.
+#pragma unroll
+            for (int g = 0; g < NGROUP; ++g) {
+                c[g] = __fmul_rn(sigmoid_f32(best[g]), 1.0f);   // cls * obj, obj == 1 (nms.py:76)
+                if (((args >> (6 * g)) & 63u) != 0 && sigmoid_f32(before[g]) == c[g]) ties |= 1u << g;
+            }
             const int pos = p0 + lane;
             finish_tile(p, lv, b, pos, pos < lv.hw, c, args, ties, lane);
             LP_PF(2);
         }
         LP_PF_OUT();
-    } else {                                             // ---- scanners: warp g owns class group g
+    } else {                                             // ---- scanners: warp w owns half (w & 1) of group w >> 1
         LP_PF_DECL;
         for (int it = 0; it < n_my; ++it) {
             const int s = it % KT_RING;
@@ -189,20 +216,17 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             if (lane == 0) mbar_wait(&full[s], (it / KT_RING) & 1);
             __syncwarp();
             LP_PF(1);               // a real barrier for the compiler too: no stage read may move above it
-            const float* col0 = stage0 + s * KT_STAGE_FLOATS + (group_begin(warp) - 13) * DEC_TILE + lane;
+            const int g = warp >> 1, half = warp & 1;
+            const float* col0 = stage0 + s * KT_STAGE_FLOATS + (group_begin(g) - 13) * DEC_TILE + lane;
             float best, before;
             int arg;
-            if (warp == 0) group_scan_smem<31>(col0, best, arg, before);
-            else if (warp == 1) group_scan_smem<24>(col0, best, arg, before);
-            else group_scan_smem<37>(col0, best, arg, before);
-            //   score: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
-            //   tie:   arg is the first index of the maximum LOGIT; the reference takes the first index of
-            //          the maximum SIGMOID, which is earlier iff a smaller logit before it rounds to the
-            //          same value -- checked exactly with one more sigmoid.
-            const float cg = __fmul_rn(sigmoid_f32(best), 1.0f);   // cls * obj, obj == 1 (nms.py:76)
-            const unsigned tie = (arg > 0 && sigmoid_f32(before) == cg) ? 1u : 0u;
-            part_c[(s * NGROUP + warp) * DEC_TILE + lane] = cg;
-            part_a[(s * NGROUP + warp) * DEC_TILE + lane] = (unsigned)arg | (tie << 8);
+            if (g == 0) half_scan_smem<31>(col0, half, best, arg, before);
+            else if (g == 1) half_scan_smem<24>(col0, half, best, arg, before);
+            else half_scan_smem<37>(col0, half, best, arg, before);
+            const int q = (s * KT_SCANNERS + warp) * DEC_TILE + lane;
+            part_b[q] = best;
+            part_p[q] = before;
+            part_a[q] = arg;
             slot_arrive(s);             // non-blocking
             LP_PF(2);
         }
