@@ -81,8 +81,9 @@ __device__ __forceinline__ bool iou_exceeds(const float4& a, float area_a, const
     // (two roundings of 2^-24 each against a margin of 1e-6; tu well inside the normal range, so the
     // relative bounds hold).  Only the band in between -- and the degenerate cases u <= 0, u or tu not
     // finite, denormal-sized products -- take the exact quotient.
+    // succ(thr) <= thr * (1 + 2^-23) needs a normal thr as well (a denormal threshold is legal, if absurd).
     const float tu = __fmul_rn(thr_floor, u);
-    if (tu > 1e-30f && tu < 3.0e38f) {   // implies thr > 0, u > 0, both finite
+    if (thr_floor >= 1e-30f && tu > 1e-30f && tu < 3.0e38f) {   // implies u > 0, both finite
         if (inter > __fmul_rn(tu, 1.000001f)) return true;
         if (inter < __fmul_rn(tu, 0.999999f)) return false;
     }
