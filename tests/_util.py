@@ -47,3 +47,39 @@ def assert_rows_equal(got, want, what=""):
         bad = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
         r, c = bad[0]
         raise AssertionError(f"{what}: {len(bad)} differing values, first at row {r} col {c}: {got[r, c]!r} vs {want[r, c]!r}")
+
+
+IOU_BAND_THRESHOLDS = (0.45, 0.65, 0.5, 0.3, 1e-3, 0.999, 1.0, 0.0, 1e-36)
+
+
+def iou_band_pairs(iou, n=6000):
+    """``[n, 2, 290]`` head rows, one pair of equal-sized boxes per image whose IoU sits within a few
+    ulps of ``iou`` (both sides, extents over four decades): the first box has the higher score, the
+    second is suppressed iff ``(double)ovr > iou``.  numpy only, so the bits are the same everywhere."""
+    rng = np.random.default_rng(int(iou * 1e6) % 9973 + 3)
+    t = np.float32(iou)
+    if float(t) > iou:
+        t = np.nextafter(t, np.float32(-np.inf))
+    w = (10.0 ** rng.uniform(-1.0, 3.0, n)).astype(np.float32)
+    h = (10.0 ** rng.uniform(-1.0, 3.0, n)).astype(np.float32)
+    # two w x h boxes shifted in x by (w - dx): IoU = dx / (2w - dx); aim at the threshold, then nudge
+    # the shift by -24..24 ulps
+    tt = min(max(float(t), 1e-7), 1.0)
+    dx = (2.0 * w.astype(np.float64) * tt / (1.0 + tt)).astype(np.float32)
+    shift = (w - dx).astype(np.float32)
+    k = rng.integers(-24, 25, n)
+    for _ in range(24):
+        shift = np.where(k > 0, np.nextafter(shift, np.float32(np.inf)),
+                         np.where(k < 0, np.nextafter(shift, np.float32(-np.inf)), shift))
+        k = k - np.sign(k)
+    x0 = rng.uniform(0, 500, n).astype(np.float32)
+    y0 = rng.uniform(0, 500, n).astype(np.float32)
+    pred = np.zeros((n, 2, 290), np.float32)
+    cx0, cy0 = x0 + w / 2, y0 + h / 2
+    pred[:, 0, 0], pred[:, 0, 1] = cx0, cy0
+    pred[:, 1, 0], pred[:, 1, 1] = (cx0 + shift).astype(np.float32), cy0
+    pred[:, :, 2], pred[:, :, 3] = w[:, None], h[:, None]
+    pred[:, :, 4] = 1.0
+    pred[:, 0, 13:] = 0.9      # the first box wins the order
+    pred[:, 1, 13:] = 0.8
+    return torch.from_numpy(pred)

@@ -328,7 +328,21 @@ def make_targets():
     save("eval_targets", targets=src.numpy(), w=np.array(w), h=np.array(h), bs=np.array(bs), **arrays)
 
 
+def make_iou_band():
+    """Kept counts of the reference for pairs of boxes within ulps of the IoU threshold (inputs are
+    regenerated by tests/_util.iou_band_pairs, numpy only)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from _util import IOU_BAND_THRESHOLDS, iou_band_pairs
+    out = {}
+    for i, iou in enumerate(IOU_BAND_THRESHOLDS):
+        pred = iou_band_pairs(iou)
+        rows = run_ref_nms(pred, 0.25, iou, 300, chunk=64)
+        out["kept_%d" % i] = np.array([r.shape[0] for r in rows], np.int8)
+        print("   thr", iou, "suppressed fraction", float((out["kept_%d" % i] == 1).mean()))
+    save("iou_band", thresholds=np.array(IOU_BAND_THRESHOLDS, np.float64), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets", "iou_band"]
     for w in which:
         globals()["make_" + w]()

@@ -13,7 +13,8 @@ import yolo_lp_b200 as lp
 from yolo_lp_b200 import synth
 from yolo_lp_b200.nms import non_max_suppression_with_index, NmsPlan
 from oracle import lp_oracle
-from _util import golden, golden_names, split_rows, seeded_inputs, assert_rows_equal
+from _util import (golden, golden_names, split_rows, seeded_inputs, assert_rows_equal, iou_band_pairs,
+                   IOU_BAND_THRESHOLDS)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -561,42 +562,21 @@ def test_tied_scores_take_the_network_sorts_inside_a_segment(A, levels):
     _check_against_oracle(pred, 0.25, 0.45, 300, f"tied scores A={A} levels={levels}")
 
 
-@pytest.mark.parametrize("iou", [0.45, 0.65, 0.5, 0.3, 1e-3, 0.999, 1.0, 0.0, 1e-36])
+@pytest.mark.parametrize("iou", IOU_BAND_THRESHOLDS)
 def test_iou_within_ulps_of_the_threshold(iou):
     """K2 decides IoU tests without the division when the quotient is clearly off the threshold and
     takes the exact IEEE quotient inside a +-1e-6 band round it.  Here every image holds one pair of
     boxes whose IoU sits within a few ulps of the threshold (both sides, many magnitudes): the kept
-    sets must still be the reference's bit for bit.  Includes thresholds whose float is the
-    degenerate input of that shortcut (0, 1, a near-denormal one)."""
-    Bn = 6000
-    rng = np.random.default_rng(int(iou * 1e6) % 9973 + 3)
-    t = np.float32(iou)
-    if float(t) > iou:
-        t = np.nextafter(t, np.float32(-np.inf))
-    w = (10.0 ** rng.uniform(-1.0, 3.0, Bn)).astype(np.float32)
-    h = (10.0 ** rng.uniform(-1.0, 3.0, Bn)).astype(np.float32)
-    # two w x h boxes shifted in x by (w - dx): IoU = dx / (2w - dx); aim at the threshold, then nudge
-    # the shift by -24..24 ulps
-    tt = min(max(float(t), 1e-7), 1.0)
-    dx = (2.0 * w.astype(np.float64) * tt / (1.0 + tt)).astype(np.float32)
-    shift = (w - dx).astype(np.float32)
-    k = rng.integers(-24, 25, Bn)
-    for _ in range(24):
-        shift = np.where(k > 0, np.nextafter(shift, np.float32(np.inf)), np.where(k < 0, np.nextafter(shift, np.float32(-np.inf)), shift))
-        k = k - np.sign(k)
-    x0 = rng.uniform(0, 500, Bn).astype(np.float32)
-    y0 = rng.uniform(0, 500, Bn).astype(np.float32)
-    pred = torch.zeros((Bn, 2, 290))
-    cx0, cy0 = x0 + w / 2, y0 + h / 2
-    pred[:, 0, 0], pred[:, 0, 1] = torch.from_numpy(cx0), torch.from_numpy(cy0)
-    pred[:, 1, 0], pred[:, 1, 1] = torch.from_numpy((cx0 + shift).astype(np.float32)), torch.from_numpy(cy0)
-    pred[:, :, 2], pred[:, :, 3] = torch.from_numpy(w)[:, None], torch.from_numpy(h)[:, None]
-    pred[:, :, 4] = 1.0
-    pred[:, 0, 13:] = 0.9      # the first box wins the order
-    pred[:, 1, 13:] = 0.8
+    sets must still be the reference's bit for bit -- checked against the oracle AND against the kept
+    counts the reference itself (torchvision CPU nms) produced for these pairs
+    (tests/golden/iou_band.npz).  Includes thresholds whose float is the degenerate input of that
+    shortcut (0, 1, a near-denormal one)."""
+    pred = iou_band_pairs(iou)
     got = _check_against_oracle(pred, 0.25, iou, 300, f"iou threshold band thr={iou}")
     kept = np.array([len(g) for g in got])
-    if 0.0 < iou < 1.0 and iou > 1e-30:
+    want = golden("iou_band")["kept_%d" % IOU_BAND_THRESHOLDS.index(iou)]
+    assert np.array_equal(kept, want), "kept counts differ from the reference run"
+    if 1e-30 < iou < 1.0:
         assert 0.1 < (kept == 1).mean() < 0.9, "the pairs must straddle the threshold"
 
 

@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import lp_oracle, torch_port
-from _util import golden, golden_names, split_rows, seeded_inputs, assert_rows_equal
+from _util import (golden, golden_names, split_rows, seeded_inputs, assert_rows_equal, iou_band_pairs,
+                   IOU_BAND_THRESHOLDS)
 
 SEEDED = [n for n in golden_names("nms_cfg") + golden_names("nms_eval")]
 EDGES = golden_names("nms_edge_")
@@ -167,3 +168,14 @@ def test_prepare_targets_oracle():
     out = lp_oracle.prepare_targets(g["targets"], int(g["w"]), int(g["h"]), int(g["bs"]))
     for i, o in enumerate(out):
         assert np.array_equal(o.view(np.uint32), g[f"out{i}"].view(np.uint32)), i
+
+
+@pytest.mark.parametrize("i", range(len(IOU_BAND_THRESHOLDS)))
+def test_oracle_iou_within_ulps_of_the_threshold_matches_reference(i):
+    """Pairs of boxes whose IoU sits within a few ulps of the threshold: the oracle's float-IoU vs
+    double-threshold compare must reproduce the kept counts of the reference run (torchvision CPU)."""
+    iou = IOU_BAND_THRESHOLDS[i]
+    pred = iou_band_pairs(iou, 6000)
+    out = lp_oracle.non_max_suppression(pred.numpy(), 0.25, iou)
+    kept = np.array([len(o) for o in out], np.int8)
+    assert np.array_equal(kept, golden("iou_band")["kept_%d" % i])
