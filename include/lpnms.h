@@ -140,6 +140,28 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
                                 lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
                                 void* done_event, void* time_begin_event, void* time_end_event);
 
+/*
+ * fp16 head tensors (the reference's --half mode: inferer.py:46-50, evaler.py:116; SURVEY §8-f rank
+ * 3).  `pred` holds B*A*290 IEEE halves, contiguous, 16-byte aligned; every value is upcast exactly
+ * on load and all arithmetic is the f32 entries', so the results are bit for bit those of the f32
+ * entry on the upcast tensor -- at half the bytes of the HBM- (and PCIe-) bound stage.  (The
+ * reference's own half mode computes in half precision on CUDA behind an unstable sort and is not
+ * reproducible across implementations; see DESIGN.md.)  Outputs, workspace and knobs as above.
+ */
+LP_API int lp_nms_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                      const float* rescale, int do_round, lp_stream_t stream);
+LP_API int lp_nms_filter_f16(const void* pred, int B, int A, double conf_thres, void* workspace,
+                             size_t workspace_bytes, lp_stream_t stream);
+LP_API int lp_nms_suppress_f16(const void* pred, int B, int A, double iou_thres, int max_det, int max_nms,
+                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                               const float* rescale, int do_round, lp_stream_t stream);
+LP_API int lp_nms_pipelined_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
+                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                void* done_event, void* time_begin_event, void* time_end_event);
+
 /* Debug / property tests: the decode kernel's sigmoid evaluated on a flat device array. */
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream);
 

@@ -580,6 +580,50 @@ def test_iou_within_ulps_of_the_threshold(iou):
         assert 0.1 < (kept == 1).mean() < 0.9, "the pairs must straddle the threshold"
 
 
+# ------------------------------------------------------------------ fp16 head tensors
+def _half_case(B, A, n_pos, seed, quant=None):
+    pred = synth.synth_head(B, A, 640, 24, n_pos, seed=seed, quant=quant)
+    return pred.half()
+
+
+@pytest.mark.parametrize("B,A,n_pos,conf,iou,max_det", [
+    (4, 8400, 300, 0.25, 0.45, 300),
+    (2, 8400, 300, 0.001, 0.65, 300),     # every anchor a candidate
+    (3, 315, 40, 0.05, 0.45, 300),        # odd A: rows only 4-byte aligned, ragged 64-row tiles
+    (5, 33, 10, 0.05, 0.5, 7),            # A < 64: several images per tile
+    (1, 33600, 4096, 0.25, 0.45, 300),
+    (2, 2100, 2100, 0.0, 0.3, 1500),      # more kept rows than one gather batch
+])
+def test_half_head_tensor_equals_fp32_path_on_the_upcast_tensor(B, A, n_pos, conf, iou, max_det):
+    """fp16 storage, exact upcast on load, fp32 arithmetic: kept anchors and all 28 columns must be
+    bit for bit those of the oracle (and of the fp32 kernels) on ``pred.float()`` -- through the serial
+    entry, the two-stream pipeline and the host-buffer path."""
+    from yolo_lp_b200.nms import NmsPipeline, non_max_suppression_with_index
+    ph = _half_case(B, A, n_pos, seed=70 + B)
+    up = ph.float()
+    want, widx = lp_oracle.non_max_suppression(up.numpy(), conf, iou, max_det=max_det, return_index=True)
+    rows, idx = non_max_suppression_with_index(ph.to(DEV), conf, iou, max_det)
+    rows32, idx32 = non_max_suppression_with_index(up.to(DEV), conf, iou, max_det)
+    for b in range(B):
+        assert np.array_equal(idx[b].cpu().numpy(), widx[b]), f"half[{b}]: kept anchors differ from the oracle"
+        assert_rows_equal(rows[b].cpu().numpy(), want[b], f"half[{b}]")
+        assert torch.equal(rows[b], rows32[b]) and torch.equal(idx[b], idx32[b])
+    # pipelined entry (lp_nms_pipelined_f16), three submissions so the re-armed workspace is exercised
+    pipe = NmsPipeline(B, A, max_det, torch.device(DEV))
+    dev_h = ph.to(DEV)
+    pipe.start()
+    for _ in range(3):
+        slot, out, counts = pipe.submit(dev_h, conf, iou)
+    pipe.finish()
+    torch.cuda.synchronize()
+    for b, k in enumerate(counts.cpu().tolist()):
+        assert_rows_equal(out[b, :k].cpu().numpy(), want[b], f"half pipelined[{b}]")
+    # host-buffer path: the halves travel as halves
+    host = lp.non_max_suppression(ph, conf, iou, max_det=max_det)
+    for b in range(B):
+        assert_rows_equal(host[b].numpy(), want[b], f"half host path[{b}]")
+
+
 def test_heavy_suppression_walks_many_segments():
     """Few tight clusters, every anchor a candidate: far fewer than max_det boxes survive, so the
     greedy walk has to consume every score segment (and every window) of the 8400 candidates."""

@@ -40,6 +40,14 @@ SIGNATURES = {
     "lp_nms_filter_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
     "lp_nms_suppress_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_nms_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "lp_nms_pipelined_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lp_nms_filter_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+    "lp_nms_suppress_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "lp_debug_nms_timing": (c_int, [c_void_p]),
     "lp_tune": (c_int, [c_int, c_int]),
     "lp_debug_sigmoid_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),

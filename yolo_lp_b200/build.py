@@ -19,7 +19,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "filter.cu", "nms.cu", "decode.cu", "decode_tma.cu", "fused.cu", "fused_tma.cu", "geometry.cu"]
+SOURCES = ["api.cu", "filter.cu", "filter_half.cu", "nms.cu", "decode.cu", "decode_tma.cu", "fused.cu", "fused_tma.cu", "geometry.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "level_tiles.cuh", os.path.join("..", "..", "include", "lpnms.h")]
 LIB = os.path.join(HERE, "liblpnms.so")
 

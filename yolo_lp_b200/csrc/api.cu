@@ -152,6 +152,7 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
     n.timing = g_debug_timing;
     n.from_levels = 0;
+    n.half_input = 0;
     n.rearm = 0;
     n.rec = reinterpret_cast<const float*>(ws + w.rec);           // only valid in a fused-size workspace
     n.slot_of = reinterpret_cast<const unsigned*>(ws + w.slot_of);
@@ -161,7 +162,7 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
 // armed: the last kernel that ran on this workspace was a K2 launched with rearm (it zeroed the
 // candidate counts and the tile counter), so the memset node in front of the filter kernel is skipped
 static int nms_filter(const float* pred, int B, int A, double conf_thres, void* workspace, size_t workspace_bytes,
-                      lp_stream_t stream, bool armed) {
+                      lp_stream_t stream, bool armed, bool half = false) {
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     FilterParams f;
     NmsParams n;
@@ -182,7 +183,7 @@ static int nms_filter(const float* pred, int B, int A, double conf_thres, void* 
     int ctas = num_sms_cached();
     ctas -= B < ctas / 2 ? B : ctas / 2;
     if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < num_sms_cached() ? g_filter_cta_limit : num_sms_cached();
-    return (int)launch_filter(f, ctas, s);
+    return (int)(half ? launch_filter_half(f, ctas, s) : launch_filter(f, ctas, s));
 }
 
 LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
@@ -192,7 +193,7 @@ LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres,
 
 static int nms_suppress(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms, void* workspace,
                         size_t workspace_bytes, float* out, int* counts, int* kept_anchor, const float* rescale,
-                        int do_round, lp_stream_t stream, bool rearm) {
+                        int do_round, lp_stream_t stream, bool rearm, bool half = false) {
     if (!counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0) return LP_E_SIZE;
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
@@ -212,6 +213,7 @@ static int nms_suppress(const float* pred, int B, int A, double iou_thres, int m
     n.rescale = rescale;
     n.do_round = do_round;
     n.rearm = rearm ? 1 : 0;
+    n.half_input = half ? 1 : 0;
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
@@ -222,11 +224,11 @@ LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres
                         rescale, do_round, stream, false);
 }
 
-LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
-                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
-                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                void* done_event, void* time_begin_event, void* time_end_event) {
+static int nms_pipelined(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                         void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                         const float* rescale, int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
+                         void* workspace_free_event, void* filtered_event, void* done_event, void* time_begin_event,
+                         void* time_end_event, bool half) {
     if (!filtered_event) return LP_E_NULL;
     cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
     cudaError_t e;
@@ -239,7 +241,7 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
         if (e != cudaSuccess) return (int)e;
     }
     // a workspace that comes with the done_event of its previous step was re-armed by that step's K2
-    int rc = nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream, workspace_free_event != nullptr);
+    int rc = nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream, workspace_free_event != nullptr, half);
     if (rc != LP_OK) return rc;
     if (time_end_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
@@ -250,13 +252,58 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
     e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
     if (e != cudaSuccess) return (int)e;
     rc = nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
-                      rescale, do_round, nms_stream, true);
+                      rescale, do_round, nms_stream, true, half);
     if (rc != LP_OK) return rc;
     if (done_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
         if (e != cudaSuccess) return (int)e;
     }
     return LP_OK;
+}
+
+LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
+                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                void* done_event, void* time_begin_event, void* time_end_event) {
+    return nms_pipelined(pred, B, A, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                         kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event, filtered_event,
+                         done_event, time_begin_event, time_end_event, false);
+}
+
+// ---- fp16 head tensors: pred holds IEEE halves, results == the f32 entries on pred.float()
+LP_API int lp_nms_filter_f16(const void* pred, int B, int A, double conf_thres, void* workspace, size_t workspace_bytes,
+                             lp_stream_t stream) {
+    return nms_filter(static_cast<const float*>(pred), B, A, conf_thres, workspace, workspace_bytes, stream, false, true);
+}
+LP_API int lp_nms_suppress_f16(const void* pred, int B, int A, double iou_thres, int max_det, int max_nms, void* workspace,
+                               size_t workspace_bytes, float* out, int* counts, int* kept_anchor, const float* rescale,
+                               int do_round, lp_stream_t stream) {
+    return nms_suppress(static_cast<const float*>(pred), B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                        counts, kept_anchor, rescale, do_round, stream, false, true);
+}
+LP_API int lp_nms_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                      const float* rescale, int do_round, lp_stream_t stream) {
+    // validate everything before queueing anything
+    if (!pred || !workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (!size_ok(B, A, max_det) || max_nms <= 0) return LP_E_SIZE;
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
+    int rc = lp_nms_filter_f16(pred, B, A, conf_thres, workspace, workspace_bytes, stream);
+    if (rc != LP_OK) return rc;
+    return lp_nms_suppress_f16(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                               rescale, do_round, stream);
+}
+LP_API int lp_nms_pipelined_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
+                                int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                void* done_event, void* time_begin_event, void* time_end_event) {
+    return nms_pipelined(static_cast<const float*>(pred), B, A, conf_thres, iou_thres, max_det, max_nms, workspace,
+                         workspace_bytes, out, counts, kept_anchor, rescale, do_round, filter_stream, nms_stream,
+                         workspace_free_event, filtered_event, done_event, time_begin_event, time_end_event, true);
 }
 
 LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) {

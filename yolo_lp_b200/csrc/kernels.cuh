@@ -19,6 +19,8 @@ struct FilterParams {
     unsigned* tile_counter;       // dynamic tile scheduler, zeroed before launch
 };
 cudaError_t launch_filter(const FilterParams& p, int num_sms, cudaStream_t stream);
+// the same for a head tensor stored as IEEE half (p.pred then points at halves); filter_half.cu
+cudaError_t launch_filter_half(const FilterParams& p, int num_sms, cudaStream_t stream);
 
 // ---- decode.cu ---------------------------------------------------------------------------------
 constexpr int DEC_TILE = 32;      // anchor positions per tile
@@ -100,6 +102,7 @@ struct NmsParams {
     long long* timing;          // debug only: [B, 16] clock64 stamps per phase, or null
     // fused path only (from_levels != 0): KF left the finished rows of every candidate, pred is null
     int from_levels;
+    int half_input;             // pred holds IEEE halves (580-byte rows), upcast exactly on load
     int rearm;                  // pipelined entries: zero counts[b] / the tile counter once read, so the
                                 // next filter launch on this workspace needs no memset node
     const float* rec;           // [B, A, 28] by slot

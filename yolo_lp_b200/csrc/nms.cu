@@ -33,6 +33,8 @@
 //           nms.py:76-96 (group maxima with first-index argmax), one per (row, coordinate) emits the
 //           xyxy box and the corners, optionally mapped back to source coordinates
 //           (inferer.py:203-228, :100).
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace lp {
@@ -179,8 +181,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // xyxy box of a candidate (nms.py:79): from the head tensor, or -- fused path -- from the finished
 // row KF stored for it
-template <bool kLevels>
+// (kHalf: the head tensor is stored as IEEE half, 580-byte rows, every value upcast exactly on load)
+template <bool kLevels, bool kHalf>
 __device__ __forceinline__ float4 candidate_box(const NmsParams& p, const float* pred, unsigned b, unsigned anchor) {
+    if (!kLevels && kHalf) {
+        const __half2* r = reinterpret_cast<const __half2*>(reinterpret_cast<const __half*>(pred) + (size_t)anchor * ROW);
+        const float2 c = __half22float2(__ldg(r)), s = __half22float2(__ldg(r + 1));
+        return xywh_to_xyxy(c.x, c.y, s.x, s.y);
+    }
     if (!kLevels) {
         const float2* r = reinterpret_cast<const float2*>(pred + (size_t)anchor * ROW);
         const float2 c = __ldg(r), s = __ldg(r + 1);
@@ -190,7 +198,7 @@ __device__ __forceinline__ float4 candidate_box(const NmsParams& p, const float*
     return __ldg(reinterpret_cast<const float4*>(p.rec + ((size_t)b * p.A + slot) * OUTW));
 }
 
-template <bool kLevels>
+template <bool kLevels, bool kHalf>
 __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);  // sort buffer, later row staging
@@ -208,7 +216,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
 
     const unsigned b = blockIdx.x;
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    const float* pred = kLevels ? nullptr : p.pred + (size_t)b * p.A * ROW;
+    // image base; with kHalf `pred` points at halves, so the element offset counts 2-byte units
+    const float* pred = kLevels ? nullptr
+                                : kHalf ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(p.pred) + (size_t)b * p.A * ROW)
+                                        : p.pred + (size_t)b * p.A * ROW;
+    constexpr int ELEM = kHalf ? 2 : 4;
     float4* kept_box = p.kept_box + (size_t)b * p.max_det;
     int* kept_anchor = p.kept_anchor_ws + (size_t)b * p.max_det;
 
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
             if (tid < n_win) {
                 const unsigned pos = w0 + tid;
                 const unsigned anchor = (unsigned)(sorted_global ? __ldcg(sorted + pos) : sorted[pos]);
-                wbox[tid] = candidate_box<kLevels>(p, pred, b, anchor);  // nms.py:79
+                wbox[tid] = candidate_box<kLevels, kHalf>(p, pred, b, anchor);  // nms.py:79
                 wanchor[tid] = (int)anchor;
             }
             __syncthreads();
@@ -501,9 +513,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                         // the gather will want this row: start pulling it into L2 now (K1 streamed the
                         // head tensor with an evict-first policy, so it is most likely back in HBM)
                         if (!kLevels) {
-                            const char* row = reinterpret_cast<const char*>(pred + (size_t)anchor * ROW);
+                            const char* row = reinterpret_cast<const char*>(pred) + (size_t)anchor * ROW * ELEM;
 #pragma unroll
-                            for (int o = 0; o < ROW * 4 + 127; o += 128) prefetch_l2(row + o);
+                            for (int o = 0; o < ROW * ELEM + 127; o += 128) prefetch_l2(row + o);
                         }
                     }
                     if (lane == 0) s_misc[2] = K;
@@ -542,11 +554,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
     // index in the head tensor (b * A + anchor) is odd, so that source (row index * 1160 B from a
     // 16-byte aligned base: 16-byte aligned only for even rows) and destination agree mod 16 and all
     // but 8 of the 1160 bytes move as 16-byte cp.async copies.
-    constexpr int SROW_BYTES = 1168;
+    // (kHalf: 580-byte rows, 4-byte aligned; slots of 584 B filled with 4-byte copies.)
+    constexpr int SROW_BYTES = kHalf ? 584 : 1168;
     unsigned char* sbytes = smem_raw;
     const int cap_rows = (int)(((size_t)p.sort_smem_keys * sizeof(unsigned long long)) / SROW_BYTES);
     const int img_parity = (int)(((size_t)b * p.A) & 1);
-#define LP_SROW(r, anchor) reinterpret_cast<const float*>(sbytes + (size_t)(r) * SROW_BYTES + 8 * (((anchor) + img_parity) & 1))
+#define LP_SROW(r, anchor) (sbytes + (size_t)(r) * SROW_BYTES + (kHalf ? 0 : 8 * (((anchor) + img_parity) & 1)))
+    // column c of a staged row, upcast exactly when the tensor is half
+    auto col = [](const unsigned char* row, int c) -> float {
+        return kHalf ? __half2float(reinterpret_cast<const __half*>(row)[c]) : reinterpret_cast<const float*>(row)[c];
+    };
     const bool do_rescale = p.rescale != nullptr;
     float pad_x = 0.f, pad_y = 0.f, ratio = 1.f, w0f = 0.f, h0f = 0.f;
     if (do_rescale) {
@@ -559,8 +576,13 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
             for (int r = (int)(tid >> 5); r < nb; r += NMS_THREADS / 32) {  // one warp per row
                 const int k = base + r;
                 const int anchor = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(pred) + (size_t)anchor * ROW * ELEM;
+                if (kHalf) {
+                    unsigned char* dst = sbytes + (size_t)r * SROW_BYTES;
+                    for (int c = (int)lane; c < ROW / 2; c += 32) cp_async_4(dst + 4 * c, src + 4 * c);
+                    continue;
+                }
                 const int odd = (anchor + img_parity) & 1;
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(pred + (size_t)anchor * ROW);
                 unsigned char* dst = sbytes + (size_t)r * SROW_BYTES + 8 * odd;
                 // 72 16-byte chunks from the first 16-byte boundary of the row, 8 bytes before (odd) or after (even)
                 for (int c = (int)lane; c < 72; c += 32) cp_async_16(dst + 8 * odd + 16 * c, src + 8 * odd + 16 * c);
@@ -587,10 +609,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
         for (int t = tid; t < nb * NGROUP; t += NMS_THREADS) {
             const int r = t >> 3, g = t & 7;
             const int ka = base + r < KEPT_SMEM ? kanchor[base + r] : kept_anchor[base + r];
-            const float* row = LP_SROW(r, ka);
-            const float obj = row[4];
+            const unsigned char* row = LP_SROW(r, ka);
+            const float obj = col(row, 4);
             const int s = group_begin(g), e = group_begin(g + 1);
-            float best = __fmul_rn(row[s], obj);  // nms.py:76
+            float best = __fmul_rn(col(row, s), obj);  // nms.py:76
             int bi = 0;
             // The SM is issue-bound here (32 warps, ~280 element visits each): keep the visit short.
             // Columns past the group's end are replaced by the group's first value -- never '>' the
@@ -602,7 +624,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = i0 + u;
-                    const float v = i < e ? __fmul_rn(row[i], obj) : first;
+                    const float v = i < e ? __fmul_rn(col(row, i), obj) : first;
                     bi = v > best ? i - s : bi;
                     best = fmaxf(best, v);
                 }
@@ -621,7 +643,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_kernel(const NmsParams p) 
                 val = c == 0 ? bx.x : c == 1 ? bx.y : c == 2 ? bx.z : bx.w;
             } else {
                 const int ka = k < KEPT_SMEM ? kanchor[k] : kept_anchor[k];
-                val = LP_SROW(r, ka)[c + 1];  // corners: columns 5..12 -> output 4..11 (nms.py:94)
+                val = col(LP_SROW(r, ka), c + 1);  // corners: columns 5..12 -> output 4..11 (nms.py:94)
             }
             if (do_rescale)
                 val = (c & 1) ? rescale_coord(val, pad_y, ratio, h0f, p.do_round) : rescale_coord(val, pad_x, ratio, w0f, p.do_round);
@@ -646,13 +668,15 @@ cudaError_t launch_nms(const NmsParams& p, int B, cudaStream_t stream) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(nms_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    if (p.from_levels) nms_kernel<true><<<B, NMS_THREADS, smem, stream>>>(p);
-    else nms_kernel<false><<<B, NMS_THREADS, smem, stream>>>(p);
+    if (p.from_levels) nms_kernel<true, false><<<B, NMS_THREADS, smem, stream>>>(p);
+    else if (p.half_input) nms_kernel<false, true><<<B, NMS_THREADS, smem, stream>>>(p);
+    else nms_kernel<false, false><<<B, NMS_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -18,16 +18,18 @@ _CHUNK_BYTES = 48 << 20  # ~48 MiB per H2D chunk: long enough for full PCIe rate
 
 
 class HostPipeline:
-    def __init__(self, B: int, A: int, max_det: int, device=None, chunk_images: int | None = None):
+    def __init__(self, B: int, A: int, max_det: int, device=None, chunk_images: int | None = None,
+                 dtype: torch.dtype = torch.float32):
         _abi.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.B, self.A, self.max_det = B, A, max_det
-        per_image = A * ROW * 4
+        self.dtype = dtype                      # fp16 head tensors travel and are read as halves
+        per_image = A * ROW * (2 if dtype == torch.float16 else 4)
         c = chunk_images or max(1, min(B, _CHUNK_BYTES // per_image))
         self.chunk = c
         self.n_chunks = (B + c - 1) // c
         with torch.cuda.device(self.device):
-            self.stage = [torch.empty((c, A, ROW), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.stage = [torch.empty((c, A, ROW), dtype=dtype, device=self.device) for _ in range(2)]
             self.plans = [NmsPlan(c, A, max_det, self.device) for _ in range(2)]
             self.tail_plan = None
             if B % c:
@@ -44,9 +46,10 @@ class HostPipeline:
         self.d2h_bytes = self.out_host.numel() * 4 + self.counts_host.numel() * 4
 
     def run(self, prediction: torch.Tensor, conf_thres: float, iou_thres: float):
-        """prediction: CPU fp32 ``[B, A, 290]``.  Returns a list of CPU tensors ``[k_b, 28]``."""
-        if prediction.dtype != torch.float32 or not prediction.is_contiguous():
-            prediction = prediction.float().contiguous()
+        """prediction: CPU fp32 (or fp16, for a pipeline built with ``dtype=torch.float16``)
+        ``[B, A, 290]``.  Returns a list of CPU tensors ``[k_b, 28]``."""
+        if prediction.dtype != self.dtype or not prediction.is_contiguous():
+            prediction = prediction.to(self.dtype).contiguous()
         c = self.chunk
         with torch.cuda.device(self.device):
             caller = torch.cuda.current_stream(self.device)
@@ -78,11 +81,11 @@ class HostPipeline:
 _pipes: dict = {}
 
 
-def host_pipeline(B: int, A: int, max_det: int) -> HostPipeline:
-    key = (B, A, max_det, torch.cuda.current_device())
+def host_pipeline(B: int, A: int, max_det: int, dtype: torch.dtype = torch.float32) -> HostPipeline:
+    key = (B, A, max_det, torch.cuda.current_device(), dtype)
     pipe = _pipes.get(key)
     if pipe is None:
         if len(_pipes) > 4:
             _pipes.clear()
-        pipe = _pipes[key] = HostPipeline(B, A, max_det)
+        pipe = _pipes[key] = HostPipeline(B, A, max_det, dtype=dtype)
     return pipe

@@ -22,6 +22,13 @@ from . import _abi
 ROW, OUT, MAX_NMS = _abi.ROW, _abi.OUT, _abi.MAX_NMS
 
 
+def _entry(stem: str, pred: torch.Tensor) -> str:
+    """C entry for the tensor's storage type: fp16 head tensors (the reference's ``--half`` mode,
+    inferer.py:46-50) are read natively -- every value upcast exactly on load -- so the result is
+    bit for bit that of the fp32 entry on ``pred.float()`` at half the bytes."""
+    return stem + ("_f16" if pred.dtype == torch.float16 else "_f32")
+
+
 def _check_thresholds(conf_thres, iou_thres):
     # nms.py:57-58, same messages
     assert 0 <= conf_thres <= 1, f'conf_thresh must be in 0.0 to 1.0, however {conf_thres} is provided.'
@@ -53,16 +60,16 @@ class NmsPlan:
 
     def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, rescale: torch.Tensor | None = None,
             do_round: bool = False, out=None, counts=None):
-        """Enqueue filter + NMS over ``pred[B,A,290]`` (CUDA, fp32, contiguous)."""
-        if pred.device != self.device or pred.dtype != torch.float32 or not pred.is_contiguous():
-            raise ValueError("pred must be a contiguous fp32 tensor on the plan's device")
+        """Enqueue filter + NMS over ``pred[B,A,290]`` (CUDA, fp32 or fp16, contiguous)."""
+        if pred.device != self.device or pred.dtype not in (torch.float32, torch.float16) or not pred.is_contiguous():
+            raise ValueError("pred must be a contiguous fp32 / fp16 tensor on the plan's device")
         if tuple(pred.shape) != (self.B, self.A, ROW):
             raise ValueError(f"pred shape {tuple(pred.shape)} != {(self.B, self.A, ROW)}")
         out = self.out if out is None else out
         counts = self.counts if counts is None else counts
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            _abi.call("lp_nms_f32", pred.data_ptr(), self.B, self.A, float(conf_thres), float(iou_thres),
+            _abi.call(_entry("lp_nms", pred), pred.data_ptr(), self.B, self.A, float(conf_thres), float(iou_thres),
                       self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
                       out.data_ptr(), counts.data_ptr(),
                       self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
@@ -72,7 +79,7 @@ class NmsPlan:
     def run_filter(self, pred: torch.Tensor, conf_thres: float):
         """Stage K1 only (lp_nms_filter_f32): candidates + counts are left in the workspace."""
         with torch.cuda.device(self.device):
-            _abi.call("lp_nms_filter_f32", pred.data_ptr(), self.B, self.A, float(conf_thres),
+            _abi.call(_entry("lp_nms_filter", pred), pred.data_ptr(), self.B, self.A, float(conf_thres),
                       self.workspace.data_ptr(), self.workspace.numel(),
                       torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -81,7 +88,7 @@ class NmsPlan:
         out = self.out if out is None else out
         counts = self.counts if counts is None else counts
         with torch.cuda.device(self.device):
-            _abi.call("lp_nms_suppress_f32", pred.data_ptr(), self.B, self.A, float(iou_thres), self.max_det,
+            _abi.call(_entry("lp_nms_suppress", pred), pred.data_ptr(), self.B, self.A, float(iou_thres), self.max_det,
                       self.max_nms, self.workspace.data_ptr(), self.workspace.numel(), out.data_ptr(),
                       counts.data_ptr(), self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
                       rescale.data_ptr() if rescale is not None else None, int(bool(do_round)),
@@ -128,7 +135,7 @@ class NmsPipeline:
             for ev in timing:  # torch creates the cudaEvent_t lazily, on the first record
                 if ev.cuda_event == 0:
                     ev.record(self.s_filter)
-        _abi.call("lp_nms_pipelined_f32", pred.data_ptr(), plan.B, plan.A, float(conf_thres), float(iou_thres),
+        _abi.call(_entry("lp_nms_pipelined", pred), pred.data_ptr(), plan.B, plan.A, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
                   self.done[slot].cuda_event if self.n >= len(self.plans) else None,
@@ -160,7 +167,7 @@ def _plan_for(B, A, max_det, device, want_anchor=False) -> NmsPlan:
 
 def _device_input(prediction: torch.Tensor) -> torch.Tensor:
     p = prediction
-    if p.dtype != torch.float32:
+    if p.dtype not in (torch.float32, torch.float16):
         p = p.float()
     if not p.is_contiguous() or p.data_ptr() % 16:
         p = p.contiguous()
@@ -188,7 +195,8 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         return [torch.zeros((0, OUT), device=prediction.device)] * B
     if prediction.device.type == "cpu":
         from .host import host_pipeline
-        return host_pipeline(B, A, max_det).run(prediction, conf_thres, iou_thres)
+        dtype = torch.float16 if prediction.dtype == torch.float16 else torch.float32
+        return host_pipeline(B, A, max_det, dtype).run(prediction, conf_thres, iou_thres)
     pred = _device_input(prediction)
     plan = _plan_for(B, A, int(max_det), pred.device)
     out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
