@@ -6,7 +6,7 @@
 //   order   keys (score desc, anchor asc) from K1.  Ascending key order reproduces torchvision's
 //           stable descending sort over the anchor-ordered compaction (nms.py:97,121); more than
 //           max_nms candidates are cut to the first max_nms (nms.py:115-116).
-//             N <= 384    rank sort in shared memory (rank = number of smaller keys)
+//             N <= 64     rank sort in shared memory (rank = number of smaller keys)
 //             larger      SEGMENTED: a 1024-bin histogram over the score bits splits the candidates
 //                         into score-ordered segments of >= 512 keys; only the segments the greedy
 //                         walk actually reaches are ordered (with max_det = 300 that is usually the
@@ -43,7 +43,7 @@ constexpr int NMS_THREADS = 1024;
 constexpr int WIN = 512;               // candidates per window
 constexpr int SORT_SMEM_KEYS = 16384;  // 128 KB sort buffer (later the row staging area)
 constexpr int BLOCK_SORT_MAX = 1024;   // block_sort: input keys [0, n), output keys [BLOCK_SORT_MAX, BLOCK_SORT_MAX + n)
-constexpr int RANK_SORT_N = 384;       // up to here the n^2 rank sort (one pass, three barriers) beats the network
+constexpr int RANK_SORT_N = 64;        // up to here the n^2 rank sort (one pass, three barriers); above, the histogram path
 constexpr int HIST_BINS = 1024;
 constexpr int SEG_TARGET = 512;        // minimum candidates per segment
 constexpr int COUNTING_BIN_MAX = 128;  // a segment whose bins are all this small is ordered by counting sort
