@@ -187,4 +187,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tensor_m
         : "memory");
 }
 
+// Host side: opt a kernel into its dynamic shared-memory size once per device (the call is idempotent,
+// so a race between two host threads only repeats it).
+template <class Kernel>
+inline cudaError_t configure_smem_once(Kernel kernel, int bytes, bool (&done)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+}
+
 }  // namespace lp

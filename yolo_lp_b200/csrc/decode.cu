@@ -102,7 +102,8 @@ cudaError_t launch_decode(const DecodeParams& p, const DecodeMaps* maps, int num
     if (p.n_tiles <= 0) return cudaSuccess;
     if (p.bulk_in == 2 && maps != nullptr) return launch_decode_tma(p, *maps, num_sms, stream);
     static_assert(DEC_SMEM <= 227 * 1024, "decode stages exceed shared memory");
-    cudaError_t e = cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM);
+    static bool configured[64] = {false};
+    cudaError_t e = configure_smem_once(decode_kernel, DEC_SMEM, configured);
     if (e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     decode_kernel<<<grid, DEC_THREADS, DEC_SMEM, stream>>>(p);

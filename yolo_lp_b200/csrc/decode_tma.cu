@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tma_kernel(const DecodeP
 
 cudaError_t launch_decode_tma(const DecodeParams& p, const DecodeMaps& maps, int num_sms, cudaStream_t stream) {
     static_assert(DT_SMEM <= 227 * 1024, "decode stages exceed shared memory");
-    cudaError_t e = cudaFuncSetAttribute(decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM);
+    static bool configured[64] = {false};
+    cudaError_t e = configure_smem_once(decode_tma_kernel, DT_SMEM, configured);
     if (e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     decode_tma_kernel<<<grid, DT_THREADS, DT_SMEM, stream>>>(p, maps);

@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(HFILTER_THREADS, 1) filter_half_kernel(const F
 
 cudaError_t launch_filter_half(const FilterParams& p, int num_sms, cudaStream_t stream) {
     static_assert(HFILTER_SMEM <= 227 * 1024, "filter stages exceed shared memory");
-    cudaError_t e = cudaFuncSetAttribute(filter_half_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFILTER_SMEM);
+    static bool configured[64] = {false};
+    cudaError_t e = configure_smem_once(filter_half_kernel, HFILTER_SMEM, configured);
     if (e != cudaSuccess) return e;
     const unsigned n_tiles = (p.total_rows + HTILE_ROWS - 1) / HTILE_ROWS;
     FilterParams q = p;

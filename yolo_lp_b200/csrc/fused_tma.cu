@@ -237,7 +237,8 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
 cudaError_t launch_levels_filter_tma(const LevelsFilterParams& p, const DecodeMaps& maps, int num_ctas, cudaStream_t stream) {
     static_assert(KT_SMEM <= 227 * 1024, "KF stages exceed shared memory");
     static_assert(KT_RING + 1 <= 16, "one named barrier per ring slot");
-    cudaError_t e = cudaFuncSetAttribute(levels_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM);
+    static bool configured[64] = {false};
+    cudaError_t e = configure_smem_once(levels_filter_tma_kernel, KT_SMEM, configured);
     if (e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_ctas ? p.n_tiles : num_ctas;
     levels_filter_tma_kernel<<<grid, KT_THREADS, KT_SMEM, stream>>>(p, maps);
