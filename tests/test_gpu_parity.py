@@ -404,6 +404,14 @@ def test_pipeline_matches_serial_path_on_alternating_batches():
     out, counts = pipe.plans[0].run(devs[1], 0.15, 0.5)
     for b, k in enumerate(counts.cpu().tolist()):
         assert_rows_equal(out[b, :k].cpu().numpy(), wants[1][b], f"serial call on a pipeline workspace [{b}]")
+    # ... and after that serial call (which leaves the counters dirty) the pipeline must zero them again
+    pipe.start()
+    for i in range(4):
+        slot, out, counts = pipe.submit(devs[2], 0.15, 0.5)
+    pipe.finish()
+    torch.cuda.synchronize()
+    for b, k in enumerate(counts.cpu().tolist()):
+        assert_rows_equal(out[b, :k].cpu().numpy(), wants[2][b], f"pipeline after a serial call [{b}]")
 
 
 def test_filter_cta_limit_does_not_change_results():

@@ -157,8 +157,12 @@ class PostprocessPlan(_LevelTable):
         self.counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
         self.kept_anchor = (torch.empty((self.B, self.max_det), dtype=torch.int32, device=self.device)
                             if want_anchor else None)
+        # True while the last thing enqueued on this workspace was a pipelined step (whose K2 leaves the
+        # candidate counters zeroed): only then may the next pipelined step skip its memset
+        self.armed = False
 
     def run(self, conf_thres, iou_thres, rescale=None, do_round=False):
+        self.armed = False
         with torch.cuda.device(self.device):
             _abi.call("lp_detect_postprocess_f32", self.arr, self.n, self.B, float(conf_thres), float(iou_thres),
                       self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
@@ -168,6 +172,7 @@ class PostprocessPlan(_LevelTable):
         return self.out, self.counts
 
     def run_filter(self, conf_thres):
+        self.armed = False
         with torch.cuda.device(self.device):
             _abi.call("lp_detect_filter_f32", self.arr, self.n, self.B, float(conf_thres), self.max_det,
                       self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device))
@@ -218,10 +223,11 @@ class PostprocessPipeline:
         _abi.call("lp_detect_pipelined_f32", plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
-                  self.done[slot].cuda_event if self.n >= len(self.plans) else None,
+                  self.done[slot].cuda_event if plan.armed else None,
                   self.filtered[slot].cuda_event, self.done[slot].cuda_event,
                   timing[0].cuda_event if timing is not None else None,
                   timing[1].cuda_event if timing is not None else None)
+        plan.armed = True
         self.n += 1
         return slot, plan.out, plan.counts
 

@@ -57,6 +57,9 @@ class NmsPlan:
         self.counts = torch.empty((self.B,), dtype=torch.int32, device=self.device)
         self.kept_anchor = (torch.empty((self.B, self.max_det), dtype=torch.int32, device=self.device)
                             if want_anchor else None)
+        # True while the last thing enqueued on this workspace was a pipelined step (whose K2 leaves the
+        # candidate counters zeroed): only then may the next pipelined step skip its memset
+        self.armed = False
 
     def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, rescale: torch.Tensor | None = None,
             do_round: bool = False, out=None, counts=None):
@@ -67,6 +70,7 @@ class NmsPlan:
             raise ValueError(f"pred shape {tuple(pred.shape)} != {(self.B, self.A, ROW)}")
         out = self.out if out is None else out
         counts = self.counts if counts is None else counts
+        self.armed = False
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _abi.call(_entry("lp_nms", pred), pred.data_ptr(), self.B, self.A, float(conf_thres), float(iou_thres),
@@ -78,6 +82,7 @@ class NmsPlan:
 
     def run_filter(self, pred: torch.Tensor, conf_thres: float):
         """Stage K1 only (lp_nms_filter_f32): candidates + counts are left in the workspace."""
+        self.armed = False
         with torch.cuda.device(self.device):
             _abi.call(_entry("lp_nms_filter", pred), pred.data_ptr(), self.B, self.A, float(conf_thres),
                       self.workspace.data_ptr(), self.workspace.numel(),
@@ -138,10 +143,11 @@ class NmsPipeline:
         _abi.call(_entry("lp_nms_pipelined", pred), pred.data_ptr(), plan.B, plan.A, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
-                  self.done[slot].cuda_event if self.n >= len(self.plans) else None,
+                  self.done[slot].cuda_event if plan.armed else None,
                   self.filtered[slot].cuda_event, self.done[slot].cuda_event,
                   timing[0].cuda_event if timing is not None else None,
                   timing[1].cuda_event if timing is not None else None)
+        plan.armed = True
         self.n += 1
         return slot, plan.out, plan.counts
 
