@@ -194,13 +194,17 @@ class PostprocessPipeline:
     overlaps K2 of batch i.  ``plans`` are ``PostprocessPlan`` objects (one per in-flight batch, each
     bound to its own level tensors / workspace); ``submit(k)`` enqueues plan ``k % depth``."""
 
-    def __init__(self, plans):
+    def __init__(self, plans, filter_streams: int = 2):
         self.plans = list(plans)
         self.device = self.plans[0].device
         depth = len(self.plans)
+        filter_streams = max(1, min(filter_streams, depth))
         with torch.cuda.device(self.device):
             lo, hi = torch.cuda.Stream.priority_range()
-            self.s_filter = torch.cuda.Stream(self.device, priority=lo)
+            # KF launches alternate between streams so that consecutive KFs overlap drain and ramp-up
+            # (see NmsPipeline); they never share a workspace: depth >= filter_streams
+            self.s_filters = [torch.cuda.Stream(self.device, priority=lo) for _ in range(filter_streams)]
+            self.s_filter = self.s_filters[0]
             self.s_nms = torch.cuda.Stream(self.device, priority=hi)
             self.filtered = [torch.cuda.Event() for _ in range(depth)]
             self.done = [torch.cuda.Event() for _ in range(depth)]
@@ -210,19 +214,21 @@ class PostprocessPipeline:
 
     def start(self):
         cur = torch.cuda.current_stream(self.device)
-        self.s_filter.wait_stream(cur)
+        for sf in self.s_filters:
+            sf.wait_stream(cur)
         self.s_nms.wait_stream(cur)
 
     def submit(self, conf_thres, iou_thres, timing=None):
         slot = self.n % len(self.plans)
         plan = self.plans[slot]
+        s_filter = self.s_filters[self.n % len(self.s_filters)]
         if timing is not None:
             for ev in timing:
                 if ev.cuda_event == 0:
-                    ev.record(self.s_filter)
+                    ev.record(s_filter)
         _abi.call("lp_detect_pipelined_f32", plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
-                  plan.counts.data_ptr(), None, None, 0, self.s_filter.cuda_stream, self.s_nms.cuda_stream,
+                  plan.counts.data_ptr(), None, None, 0, s_filter.cuda_stream, self.s_nms.cuda_stream,
                   self.done[slot].cuda_event if plan.armed else None,
                   self.filtered[slot].cuda_event, self.done[slot].cuda_event,
                   timing[0].cuda_event if timing is not None else None,
@@ -233,7 +239,8 @@ class PostprocessPipeline:
 
     def finish(self):
         cur = torch.cuda.current_stream(self.device)
-        cur.wait_stream(self.s_filter)
+        for sf in self.s_filters:
+            cur.wait_stream(sf)
         cur.wait_stream(self.s_nms)
 
 
