@@ -30,7 +30,7 @@ def timed(fn, k=K):
     return a.elapsed_time(b) / k * 1e3
 
 
-for ctas in (0, 140, 132, 124, 116, 100, 84):
+for ctas in (0, 148, 132, 116, 100, 84):
     _abi.call("lp_tune", 0, ctas)
     t_f = timed(lambda: plan.run_filter(pred, cfg["conf"]))
     t_s = timed(lambda: plan.run(pred, cfg["conf"], cfg["iou"]))
