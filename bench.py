@@ -412,7 +412,7 @@ def run_ours(args):
     # its neighbours (consecutive K1s otherwise overlap each other's drain and ramp-up, and a bracket
     # would then measure queueing, not the kernel), which costs ~20 us of bubble per timed launch --
     # so only about ten launches of the timed region are measured this way.
-    n_timed = max(2, min(10, K // 16)) if K >= 4 else 1
+    n_timed = max(1, min(10, K // 16))
     TIME_EVERY = max(1, K // n_timed)
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in list(range(TIME_EVERY // 2, K, TIME_EVERY))[:n_timed]}   # never step 0: the pipeline is still filling
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
