@@ -472,6 +472,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": filt_avg,
                 "share_of_step": filt_avg / ms_per_step,
+                "share_of_serial_step": lat_filter / (lat_filter + lat_nms),   # the figure an ncu launch list (serialised) shows
                 "timed_launches": len(filt_ms),
                 "note": "K1 timed inside the pipelined region, K2 of the previous step running concurrently; the timed launches "
                         "(about ten per run) are fenced off from the neighbouring K1s, which otherwise overlap each other's drain and "
