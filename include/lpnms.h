@@ -200,6 +200,26 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, 
                                    lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
                                    void* done_event, void* time_begin_event, void* time_end_event);
 
+/*
+ * The fused path on fp16 level tensors (model.half(): the prediction convs emit halves).  The
+ * pointers in lp_level_t then address IEEE halves; every value is upcast exactly on load, so the
+ * results are bit for bit those of the f32 entries on the upcast tensors.  TMA kernel only: returns
+ * LP_E_ARG unless every level has h*w % 8 == 0 and 16-byte aligned tensors -- upcast such inputs and
+ * call the f32 entry.  K2 is shared: use lp_detect_suppress_f32 after lp_detect_filter_f16.
+ */
+LP_API int lp_detect_postprocess_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                     double iou_thres, int max_det, int max_nms, void* workspace,
+                                     size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                                     const float* rescale, int do_round, lp_stream_t stream);
+LP_API int lp_detect_filter_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream);
+LP_API int lp_detect_pipelined_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                   double iou_thres, int max_det, int max_nms, void* workspace,
+                                   size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                                   const float* rescale, int do_round, lp_stream_t filter_stream,
+                                   lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                   void* done_event, void* time_begin_event, void* time_end_event);
+
 /* generate_anchors(is_eval=True, mode='af'): anchor_points[A,2], stride_tensor[A]. */
 LP_API int lp_generate_anchors_f32(const int* h_host, const int* w_host, const float* stride_host, int n_levels,
                             float grid_cell_offset, float* anchor_points, float* stride_tensor, lp_stream_t stream);

@@ -632,6 +632,37 @@ def test_half_head_tensor_equals_fp32_path_on_the_upcast_tensor(B, A, n_pos, con
         assert_rows_equal(host[b].numpy(), want[b], f"half host path[{b}]")
 
 
+@pytest.mark.parametrize("B,H,W,conf", [(32, 640, 640, 0.25), (9, 640, 640, 0.001), (4, 1280, 1280, 0.25),
+                                         (5, 416, 640, 0.05), (3, 320, 320, 0.1)])
+def test_fused_path_on_half_level_tensors_equals_f32_path_on_the_upcast_tensors(B, H, W, conf):
+    """fp16 level tensors (model.half()) through lp_detect_postprocess_f16 / lp_detect_pipelined_f16:
+    exact upcast on load, so the detections must be bit for bit those of the f32 entries on the upcast
+    tensors.  320x320 has a 10x10 level (h*w % 8 != 0): the shim upcasts and takes the f32 entry."""
+    from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+    levels = synth.synth_levels(B, H, W, DEV, seed=B + W)
+    half = [{k: v.half() for k, v in lv.items()} for lv in levels]
+    up = [{k: v.float() for k, v in lv.items()} for lv in half]
+    ref = PostprocessPlan(up, (8, 16, 32), 300)
+    ref_out, ref_counts = ref.run(conf, 0.45)
+    plan = PostprocessPlan(half, (8, 16, 32), 300)
+    assert plan.half == all((lv["reg"].shape[2] * lv["reg"].shape[3]) % 8 == 0 for lv in levels)
+    plan.workspace.fill_(0xFF)
+    out, counts = plan.run(conf, 0.45)
+    torch.cuda.synchronize()
+    assert torch.equal(counts, ref_counts) and int(counts.sum()) > 0
+    for b, k in enumerate(counts.cpu().tolist()):
+        assert torch.equal(out[b, :k], ref_out[b, :k]), f"image {b}"
+    pipe = PostprocessPipeline([plan, PostprocessPlan(half, (8, 16, 32), 300)])
+    pipe.start()
+    for _ in range(5):
+        slot, out, counts = pipe.submit(conf, 0.45)
+    pipe.finish()
+    torch.cuda.synchronize()
+    assert torch.equal(counts, ref_counts)
+    for b, k in enumerate(counts.cpu().tolist()):
+        assert torch.equal(out[b, :k], ref_out[b, :k]), f"pipelined image {b}"
+
+
 def test_heavy_suppression_walks_many_segments():
     """Few tight clusters, every anchor a candidate: far fewer than max_det boxes survive, so the
     greedy walk has to consume every score segment (and every window) of the 8400 candidates."""

@@ -348,7 +348,7 @@ static EncodeTiledFn tensor_map_encoder() {
 
 // tensor maps of every level tensor for the decode kernel's TMA mode; false -> use the cp.async modes
 static bool build_decode_maps(const DecodeLevel (&lv)[LP_MAX_LEVELS], int n_levels, int B, DecodeMaps& maps,
-                              int n_tensors = DEC_TENSORS) {
+                              int n_tensors = DEC_TENSORS, bool half = false) {
     EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) return false;
     for (int l = 0; l < n_levels; ++l) {
@@ -356,10 +356,11 @@ static bool build_decode_maps(const DecodeLevel (&lv)[LP_MAX_LEVELS], int n_leve
             const int C = k == 8 ? 4 : k == 9 ? 8 : group_begin(k + 1) - group_begin(k);
             const float* base = k == 8 ? lv[l].reg : k == 9 ? lv[l].cor : lv[l].cls[k];
             const cuuint64_t dims[3] = {(cuuint64_t)lv[l].hw, (cuuint64_t)C, (cuuint64_t)B};
-            const cuuint64_t strides[2] = {(cuuint64_t)lv[l].hw * 4, (cuuint64_t)lv[l].hw * 4 * C};
+            const cuuint64_t esz = half ? 2 : 4;
+            const cuuint64_t strides[2] = {(cuuint64_t)lv[l].hw * esz, (cuuint64_t)lv[l].hw * esz * C};
             const cuuint32_t box[3] = {(cuuint32_t)DEC_TILE, (cuuint32_t)C, 1};
             const cuuint32_t estr[3] = {1, 1, 1};
-            if (encode(&maps.m[l][k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+            if (encode(&maps.m[l][k], half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return false;
@@ -432,7 +433,8 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
 // overlapped: the caller runs K2 of another batch concurrently (the pipelined entry and the stand-alone
 // stage entry, which exists for exactly that); false for the serial one-call path
 static int detect_filter(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det, void* workspace,
-                         size_t workspace_bytes, lp_stream_t stream, bool overlapped, bool armed = false) {
+                         size_t workspace_bytes, lp_stream_t stream, bool overlapped, bool armed = false,
+                         bool half = false) {
     if (max_det < 0) return LP_E_SIZE;
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     LevelsFilterParams k;
@@ -465,7 +467,18 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
     k.tile_counter = f.tile_counter;
     k.timing = g_debug_timing;
     DecodeMaps maps;
-    const bool tma = bulk && g_decode_tma && build_decode_maps(k.lv, n_levels, B, maps, NGROUP);
+    k.half_levels = half ? 1 : 0;
+    bool tma;
+    if (half) {
+        // fp16 level tensors exist as a TMA kernel only: 16-byte aligned tensors and row strides
+        // (h*w % 8 == 0 at every level); the caller upcasts anything else and takes the f32 entry
+        for (int l = 0; l < n_levels; ++l)
+            if (k.lv[l].hw % 8 != 0) return LP_E_ARG;
+        if (!bulk || !build_decode_maps(k.lv, n_levels, B, maps, NGROUP, true)) return LP_E_ARG;
+        tma = true;
+    } else {
+        tma = bulk && g_decode_tma && build_decode_maps(k.lv, n_levels, B, maps, NGROUP);
+    }
     // like K1: one persistent CTA per SM, some SMs left free for K2 of the previous batch.  The
     // register-resident kernel is latency-bound and wants more SMs than K1 (a sixth left free is the
     // measured sweet spot; K2's CTAs also fit beside it on a shared SM).  The TMA kernel fills its
@@ -515,6 +528,11 @@ static int detect_suppress(const lp_level_t* levels, int n_levels, int B, double
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
+LP_API int lp_detect_filter_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
+    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, true, false, true);
+}
+
 LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
                                   int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                   int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream) {
@@ -522,10 +540,9 @@ LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B,
                            kept_anchor, rescale, do_round, stream, false);
 }
 
-LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
-                                     int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
-                                     int* counts, int* kept_anchor, const float* rescale, int do_round,
-                                     lp_stream_t stream) {
+static int detect_postprocess(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                              int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                              int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream, bool half) {
     // validate everything before queueing anything
     if (!workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0 || max_det < 0) return LP_E_SIZE;
@@ -538,18 +555,35 @@ LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
     if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
     if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
-    rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, false);
+    rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, false, false, half);
     if (rc != LP_OK) return rc;
     return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
                                   kept_anchor, rescale, do_round, stream);
 }
 
-LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
-                                   int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
-                                   int* counts, int* kept_anchor, const float* rescale, int do_round,
-                                   lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
-                                   void* filtered_event, void* done_event, void* time_begin_event,
-                                   void* time_end_event) {
+LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                     int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                     int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                     lp_stream_t stream) {
+    return detect_postprocess(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                              counts, kept_anchor, rescale, do_round, stream, false);
+}
+// fp16 level tensors (the pointers of lp_level_t then address IEEE halves): results == the f32 entry on
+// the upcast tensors.  LP_E_ARG when a level's h*w is not a multiple of 8 or a tensor is not 16-byte
+// aligned (the fp16 path is a TMA kernel only): upcast and call the f32 entry.
+LP_API int lp_detect_postprocess_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                     int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                     int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                     lp_stream_t stream) {
+    return detect_postprocess(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                              counts, kept_anchor, rescale, do_round, stream, true);
+}
+
+static int detect_pipelined(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres, int max_det,
+                            int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                            int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                            lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event, void* done_event,
+                            void* time_begin_event, void* time_end_event, bool half) {
     if (!filtered_event) return LP_E_NULL;
     cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
     cudaError_t e;
@@ -562,7 +596,7 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B
         if (e != cudaSuccess) return (int)e;
     }
     int rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream, true,
-                           workspace_free_event != nullptr);
+                           workspace_free_event != nullptr, half);
     if (rc != LP_OK) return rc;
     if (time_end_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
@@ -580,6 +614,27 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B
         if (e != cudaSuccess) return (int)e;
     }
     return LP_OK;
+}
+
+LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                   int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                   int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                   lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
+                                   void* filtered_event, void* done_event, void* time_begin_event,
+                                   void* time_end_event) {
+    return detect_pipelined(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                            counts, kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
+                            filtered_event, done_event, time_begin_event, time_end_event, false);
+}
+LP_API int lp_detect_pipelined_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                   int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                   int* counts, int* kept_anchor, const float* rescale, int do_round,
+                                   lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
+                                   void* filtered_event, void* done_event, void* time_begin_event,
+                                   void* time_end_event) {
+    return detect_pipelined(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                            counts, kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
+                            filtered_event, done_event, time_begin_event, time_end_event, true);
 }
 
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream) {

@@ -1,22 +1,32 @@
 // Shared by the two KF kernels (fused.cu: register-resident loads, fused_tma.cu: TMA-staged loads):
 // what happens to a tile of 32 anchors once the eight group maxima / argmaxes are known.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace lp {
 
+// Element idx of a level tensor.  kHalf: the DecodeLevel pointers address IEEE halves (fp16 level
+// tensors, the reference's --half mode) and every value is upcast exactly on load.
+template <bool kHalf>
+__device__ __forceinline__ float ld_level(const float* base, size_t idx) {
+    return kHalf ? __half2float(__ldg(reinterpret_cast<const __half*>(base) + idx)) : __ldg(base + idx);
+}
+
 // Exact first argmax in sigmoid space for one group of one anchor, warp-cooperative (lanes along the
 // group's columns).  Only reached when two different logits round to the same sigmoid.
-static __device__ __noinline__ int group_argmax_exact(const float* plane, size_t hw, int width, int lane) {
+template <bool kHalf>
+static __device__ __noinline__ int group_argmax_exact(const float* base, size_t idx0, size_t hw, int width, int lane) {
     constexpr int kInvalid = 1 << 20;
     float best = -INFINITY;
     int bi = kInvalid;
     if (lane < width) {
-        best = sigmoid_f32(__ldg(plane + (size_t)lane * hw));
+        best = sigmoid_f32(ld_level<kHalf>(base, idx0 + (size_t)lane * hw));
         bi = lane;
     }
     if (lane + 32 < width) {
-        const float v = sigmoid_f32(__ldg(plane + (size_t)(lane + 32) * hw));
+        const float v = sigmoid_f32(ld_level<kHalf>(base, idx0 + (size_t)(lane + 32) * hw));
         if (v > best) { best = v; bi = lane + 32; }
     }
 #pragma unroll
@@ -31,6 +41,7 @@ static __device__ __noinline__ int group_argmax_exact(const float* plane, size_t
 // c[g] = group scores, args = eight 6-bit first-argmax indices of the maximum LOGIT, ties = groups
 // whose argmax must be re-derived in sigmoid space.  Filter (nms.py:90-91), slot claim, key, and
 // for the survivors the finished 28-float row.  Warp-collective: all 32 lanes call it.
+template <bool kHalf = false>
 __device__ __forceinline__ void finish_tile(const LevelsFilterParams& p, const DecodeLevel& lv, int b, int pos, bool valid,
                                             const float (&c)[NGROUP], unsigned long long args, unsigned ties, int lane) {
     const size_t hw = (size_t)lv.hw;
@@ -45,12 +56,10 @@ __device__ __forceinline__ void finish_tile(const LevelsFilterParams& p, const D
         // the slot claim's (an L2 atomic) instead of following it.
         float d[12];
         if (pass) {
-            const float* reg = lv.reg + off * 4 + pos;
-            const float* cor = lv.cor + off * 8 + pos;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) d[i] = __ldg(reg + i * hw);
+            for (int i = 0; i < 4; ++i) d[i] = ld_level<kHalf>(lv.reg, off * 4 + pos + i * hw);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d[4 + i] = __ldg(cor + i * hw);
+            for (int i = 0; i < 8; ++i) d[4 + i] = ld_level<kHalf>(lv.cor, off * 8 + pos + i * hw);
         }
         int base = 0;
         if (lane == 0) base = atomicAdd(p.counts + b, __popc(m));
@@ -65,7 +74,7 @@ __device__ __forceinline__ void finish_tile(const LevelsFilterParams& p, const D
             for (int g = 0; g < NGROUP; ++g) {
                 if (!((tg >> g) & 1u)) continue;  // warp-uniform
                 const int width = group_begin(g + 1) - group_begin(g);
-                const int exact = group_argmax_exact(lv.cls[g] + off * width + cpos, hw, width, lane);
+                const int exact = group_argmax_exact<kHalf>(lv.cls[g], off * width + cpos, hw, width, lane);
                 if (lane == src) args = (args & ~(63ull << (6 * g))) | ((unsigned long long)exact << (6 * g));
             }
         }
@@ -95,6 +104,7 @@ __device__ __forceinline__ void finish_tile(const LevelsFilterParams& p, const D
     }
 }
 
+// p.half_levels selects the fp16 instantiation (maps then describe FLOAT16 tensors)
 cudaError_t launch_levels_filter_tma(const LevelsFilterParams& p, const DecodeMaps& maps, int num_ctas, cudaStream_t stream);
 
 }  // namespace lp

@@ -29,6 +29,8 @@
 //                        own finisher was slow -- seen only on a cold workspace.)
 // Tiles are assigned statically (tile = blockIdx.x + it * gridDim.x): every tile costs the same here.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
+#include <type_traits>
+
 #include "fused_tile.cuh"
 
 namespace lp {
@@ -38,9 +40,10 @@ constexpr int KT_SCANNERS = 2 * NGROUP;              // warps 0..15: warp w scan
 constexpr int KT_FINISHERS = 6;                      // warps 16..21: tile t belongs to finisher t % 6
 constexpr int KT_PRODUCERS = 2;                      // warps 22..23
 constexpr int KT_THREADS = (KT_SCANNERS + KT_FINISHERS + KT_PRODUCERS) * 32;
-constexpr int KT_STAGE_FLOATS = (ROW - 13) * DEC_TILE;   // class planes only
+constexpr int KT_STAGE_ELEMS = (ROW - 13) * DEC_TILE;    // class planes only; 4 (2) bytes each
+constexpr int KT_STAGE_FLOATS = KT_STAGE_ELEMS;
 constexpr int KT_PART_WORDS = KT_SCANNERS * DEC_TILE;    // per ring slot: one word per scanner and position
-constexpr int KT_SMEM = KT_RING * (KT_STAGE_FLOATS + 3 * KT_PART_WORDS) * 4 + 2 * KT_RING * 8;
+constexpr int KT_SMEM = KT_RING * (KT_STAGE_FLOATS + 3 * KT_PART_WORDS) * 4 + 2 * KT_RING * 8;   // fp16 stages use half of theirs
 
 // Named barrier of ring slot s (1..5): the sixteen scanner warps arrive, the tile's finisher warp waits.
 // (best, arg, before) of a range, followed by the same of a LATER range of the same group
@@ -65,15 +68,32 @@ __device__ __forceinline__ void slot_wait(int s) {
 // later sub-range wins only with a strictly larger maximum, and then everything in the earlier ones
 // precedes its index.  Within a chain the running maximum is an FMNMX; the compare that drives the
 // selects hangs off it.
-template <int C0, int C1>
-__device__ __forceinline__ void range_scan_smem(const float* col0, float& best, int& arg, float& before) {
+// First channel row of class group g inside a stage.  A TMA box must land on a 128-byte boundary:
+// fp32 rows are 128 B, so the groups pack densely; fp16 rows are 64 B, so every group starts on an even
+// row (odd-width groups are followed by one unused row: 284 rows instead of 277).
+template <bool kHalf>
+__host__ __device__ constexpr int stage_row(int g) {
+    if (!kHalf) return group_begin(g) - 13;
+    int r = 0;
+    for (int i = 0; i < g; ++i) r += ((group_begin(i + 1) - group_begin(i)) + 1) & ~1;
+    return r;
+}
+constexpr int KT_STAGE_ELEMS_H = stage_row<true>(NGROUP) * DEC_TILE;   // 284 rows of 32 halves
+static_assert(KT_STAGE_ELEMS_H * 2 % 128 == 0 && KT_STAGE_ELEMS_H * 2 <= KT_STAGE_FLOATS * 4, "fp16 stage layout");
+
+// T = float or __half (stage element); a half is upcast exactly
+__device__ __forceinline__ float stage_val(const float* p) { return *p; }
+__device__ __forceinline__ float stage_val(const __half* p) { return __half2float(*p); }
+
+template <int C0, int C1, class T>
+__device__ __forceinline__ void range_scan_smem(const T* col0, float& best, int& arg, float& before) {
     constexpr int NC = 2, WIDTH = C1 - C0;
     constexpr int Q = (WIDTH + NC - 1) / NC;   // chain k covers [C0 + k*Q, min(C0 + (k+1)*Q, C1))
     float bm[NC], pm[NC];
     int am[NC];
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        bm[k] = col0[(C0 + k * Q) * DEC_TILE];
+        bm[k] = stage_val(col0 + (C0 + k * Q) * DEC_TILE);
         pm[k] = -INFINITY;
         am[k] = C0 + k * Q;
     }
@@ -82,7 +102,7 @@ __device__ __forceinline__ void range_scan_smem(const float* col0, float& best, 
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             if (k * Q + c < WIDTH) {
-                const float v = col0[(C0 + k * Q + c) * DEC_TILE];
+                const float v = stage_val(col0 + (C0 + k * Q + c) * DEC_TILE);
                 const bool up = v > bm[k];   // strict: the first occurrence of the maximum wins (torch.max)
                 pm[k] = up ? bm[k] : pm[k];
                 am[k] = up ? C0 + k * Q + c : am[k];
@@ -96,8 +116,8 @@ __device__ __forceinline__ void range_scan_smem(const float* col0, float& best, 
 #pragma unroll
     for (int k = 1; k < NC; ++k) merge_later(best, arg, before, bm[k], am[k], pm[k]);
 }
-template <int WIDTH>
-__device__ __forceinline__ void half_scan_smem(const float* col0, int half, float& best, int& arg, float& before) {
+template <int WIDTH, class T>
+__device__ __forceinline__ void half_scan_smem(const T* col0, int half, float& best, int& arg, float& before) {
     constexpr int H = WIDTH / 2;
     if (half == 0) range_scan_smem<0, H>(col0, best, arg, before);
     else range_scan_smem<H, WIDTH>(col0, best, arg, before);
@@ -123,11 +143,16 @@ __device__ __forceinline__ void locate(const LevelsFilterParams& p, int tile, in
 #define LP_PF_OUT() do { } while (0)
 #endif
 
+template <bool kHalf>
 __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const LevelsFilterParams p,
                                                                             const __grid_constant__ DecodeMaps maps) {
+    using T = typename std::conditional<kHalf, __half, float>::type;
+    constexpr int STAGE_ELEMS = kHalf ? KT_STAGE_ELEMS_H : KT_STAGE_ELEMS;
+    constexpr int stage_rows[NGROUP] = {stage_row<kHalf>(0), stage_row<kHalf>(1), stage_row<kHalf>(2), stage_row<kHalf>(3),
+                                        stage_row<kHalf>(4), stage_row<kHalf>(5), stage_row<kHalf>(6), stage_row<kHalf>(7)};
     extern __shared__ __align__(128) unsigned char smem[];
-    float* stage0 = reinterpret_cast<float*>(smem);
-    float* part_b = stage0 + KT_RING * KT_STAGE_FLOATS;                          // [ring][scanner][position] maximum logit
+    T* stage0 = reinterpret_cast<T*>(smem);
+    float* part_b = reinterpret_cast<float*>(smem) + KT_RING * KT_STAGE_FLOATS;   // same offsets for both element types                          // [ring][scanner][position] maximum logit
     float* part_p = part_b + KT_RING * KT_PART_WORDS;                            // ... largest logit before its index
     int* part_a = reinterpret_cast<int*>(part_p + KT_RING * KT_PART_WORDS);      // ... its first index in the group
     uint64_t* full = reinterpret_cast<uint64_t*>(part_a + KT_RING * KT_PART_WORDS);
@@ -154,12 +179,12 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             LP_PF(0);
             if (use > 0) mbar_wait_relaxed(&empty[s], (use - 1) & 1);
             LP_PF(1);
-            float* stage = stage0 + s * KT_STAGE_FLOATS;
+            T* stage = stage0 + s * STAGE_ELEMS;
             fence_proxy_async_smem();   // the stage was last read through the generic proxy
-            mbar_expect_tx(&full[s], KT_STAGE_FLOATS * 4);
+            mbar_expect_tx(&full[s], KT_STAGE_ELEMS * (int)sizeof(T));   // the boxes' bytes (padding rows are not written)
 #pragma unroll
             for (int g = 0; g < NGROUP; ++g)
-                tma_load_3d(stage + (group_begin(g) - 13) * DEC_TILE, &maps.m[l][g], p0, 0, b, &full[s]);
+                tma_load_3d(stage + stage_row<kHalf>(g) * DEC_TILE, &maps.m[l][g], p0, 0, b, &full[s]);
             LP_PF(2);
         }
         LP_PF_OUT();
@@ -204,7 +229,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
                 if (((args >> (6 * g)) & 63u) != 0 && sigmoid_f32(before[g]) == c[g]) ties |= 1u << g;
             }
             const int pos = p0 + lane;
-            finish_tile(p, lv, b, pos, pos < lv.hw, c, args, ties, lane);
+            finish_tile<kHalf>(p, lv, b, pos, pos < lv.hw, c, args, ties, lane);
             LP_PF(2);
         }
         LP_PF_OUT();
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             __syncwarp();
             LP_PF(1);               // a real barrier for the compiler too: no stage read may move above it
             const int g = warp >> 1, half = warp & 1;
-            const float* col0 = stage0 + s * KT_STAGE_FLOATS + (group_begin(g) - 13) * DEC_TILE + lane;
+            const T* col0 = stage0 + s * STAGE_ELEMS + stage_rows[g] * DEC_TILE + lane;
             float best, before;
             int arg;
             if (g == 0) half_scan_smem<31>(col0, half, best, arg, before);
@@ -237,11 +262,13 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
 cudaError_t launch_levels_filter_tma(const LevelsFilterParams& p, const DecodeMaps& maps, int num_ctas, cudaStream_t stream) {
     static_assert(KT_SMEM <= 227 * 1024, "KF stages exceed shared memory");
     static_assert(KT_RING + 1 <= 16, "one named barrier per ring slot");
-    static bool configured[64] = {false};
-    cudaError_t e = configure_smem_once(levels_filter_tma_kernel, KT_SMEM, configured);
+    static bool configured[64] = {false}, configured_h[64] = {false};
+    cudaError_t e = p.half_levels ? configure_smem_once(levels_filter_tma_kernel<true>, KT_SMEM, configured_h)
+                                  : configure_smem_once(levels_filter_tma_kernel<false>, KT_SMEM, configured);
     if (e != cudaSuccess) return e;
     const int grid = p.n_tiles < num_ctas ? p.n_tiles : num_ctas;
-    levels_filter_tma_kernel<<<grid, KT_THREADS, KT_SMEM, stream>>>(p, maps);
+    if (p.half_levels) levels_filter_tma_kernel<true><<<grid, KT_THREADS, KT_SMEM, stream>>>(p, maps);
+    else levels_filter_tma_kernel<false><<<grid, KT_THREADS, KT_SMEM, stream>>>(p, maps);
     return cudaGetLastError();
 }
 

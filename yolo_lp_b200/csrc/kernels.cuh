@@ -75,6 +75,7 @@ struct LevelsFilterParams {
     float* rec;                   // [B, A, 28] finished detection rows of the candidates, by slot
     unsigned* slot_of;            // [B, A] slot of a candidate anchor (only candidates are written)
     unsigned* tile_counter;       // dynamic tile scheduler, zeroed before launch
+    int half_levels;              // the level tensors hold IEEE halves (TMA kernel only)
     long long* timing;            // debug only (-DLP_KF_PROFILE builds): per-warp cycle sums, see fused_tma.cu
 };
 cudaError_t launch_levels_filter(const LevelsFilterParams& p, const DecodeMaps* maps, int num_ctas, cudaStream_t stream);

@@ -21,11 +21,11 @@ CLS_WIDTH = (31, 24, 37, 37, 37, 37, 37, 37)
 ROW = _abi.ROW
 
 
-def _cuda_f32(t: torch.Tensor, what: str) -> torch.Tensor:
+def _cuda_f32(t: torch.Tensor, what: str, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
         raise RuntimeError(f"yolo_lp_b200: {what} must be a CUDA tensor (no CPU fallback)")
-    if t.dtype != torch.float32:
-        t = t.float()
+    if t.dtype != dtype:
+        t = t.to(dtype)
     return t.contiguous()
 
 
@@ -91,10 +91,16 @@ def dist2cor(distance, anchor_points):
 class _LevelTable:
     """Validated ``lp_level_t[]`` for a fixed set of level tensors."""
 
-    def __init__(self, levels, strides):
+    def __init__(self, levels, strides, allow_half: bool = False):
         n = len(levels)
         if not 0 < n <= _abi.MAX_LEVELS or len(strides) != n:
             raise ValueError("1..4 levels with one stride each")
+        # fp16 level tensors (model.half()) stay halves when the caller has an f16 entry for them and
+        # the shapes suit it (TMA kernel only: h*w % 8 == 0 at every level); otherwise they are upcast
+        every = [t for lv in levels for t in lv.values()]
+        self.half = bool(allow_half and all(t.dtype == torch.float16 for t in every)
+                         and all((lv["reg"].shape[2] * lv["reg"].shape[3]) % 8 == 0 for lv in levels))
+        dt = torch.float16 if self.half else torch.float32
         self.arr = (_abi.LpLevel * n)()
         self.keep = []  # keeps (possibly copied) contiguous inputs alive
         self.n = n
@@ -102,16 +108,16 @@ class _LevelTable:
         self.device = levels[0]["reg"].device
         A = 0
         for i, (lv, s) in enumerate(zip(levels, strides)):
-            reg = _cuda_f32(lv["reg"], "reg")
+            reg = _cuda_f32(lv["reg"], "reg", dt)
             _, c, h, w = reg.shape
             if c != 4:
                 raise ValueError("reg must have 4 channels (use_dfl=False, reg_max=0)")
-            cor = _cuda_f32(lv["cor"], "cor")
+            cor = _cuda_f32(lv["cor"], "cor", dt)
             if tuple(cor.shape) != (B, 8, h, w):
                 raise ValueError(f"cor shape {tuple(cor.shape)}")
             self.keep += [reg, cor]
             for g, (name, width) in enumerate(zip(CLS_NAMES, CLS_WIDTH)):
-                t = _cuda_f32(lv[name], name)
+                t = _cuda_f32(lv[name], name, dt)
                 if tuple(t.shape) != (B, width, h, w):
                     raise ValueError(f"{name} shape {tuple(t.shape)} != {(B, width, h, w)}")
                 self.keep.append(t)
@@ -149,8 +155,9 @@ class PostprocessPlan(_LevelTable):
 
     def __init__(self, levels, strides=(8, 16, 32), max_det: int = 300, max_nms: int = _abi.MAX_NMS,
                  want_anchor: bool = False):
-        super().__init__(levels, strides)
+        super().__init__(levels, strides, allow_half=True)
         self.max_det, self.max_nms = int(max_det), int(max_nms)
+        self._sfx = "_f16" if self.half else "_f32"
         nbytes = _abi.detect_workspace_bytes(self.B, self.A, self.max_det)
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         self.out = torch.empty((self.B, self.max_det, _abi.OUT), dtype=torch.float32, device=self.device)
@@ -164,7 +171,7 @@ class PostprocessPlan(_LevelTable):
     def run(self, conf_thres, iou_thres, rescale=None, do_round=False):
         self.armed = False
         with torch.cuda.device(self.device):
-            _abi.call("lp_detect_postprocess_f32", self.arr, self.n, self.B, float(conf_thres), float(iou_thres),
+            _abi.call("lp_detect_postprocess" + self._sfx, self.arr, self.n, self.B, float(conf_thres), float(iou_thres),
                       self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
                       self.out.data_ptr(), self.counts.data_ptr(),
                       self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
@@ -174,7 +181,7 @@ class PostprocessPlan(_LevelTable):
     def run_filter(self, conf_thres):
         self.armed = False
         with torch.cuda.device(self.device):
-            _abi.call("lp_detect_filter_f32", self.arr, self.n, self.B, float(conf_thres), self.max_det,
+            _abi.call("lp_detect_filter" + self._sfx, self.arr, self.n, self.B, float(conf_thres), self.max_det,
                       self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device))
 
     def run_suppress(self, iou_thres, rescale=None, do_round=False):
@@ -226,7 +233,7 @@ class PostprocessPipeline:
             for ev in timing:
                 if ev.cuda_event == 0:
                     ev.record(s_filter)
-        _abi.call("lp_detect_pipelined_f32", plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
+        _abi.call("lp_detect_pipelined" + plan._sfx, plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, s_filter.cuda_stream, self.s_nms.cuda_stream,
                   self.done[slot].cuda_event if plan.armed else None,
