@@ -32,11 +32,15 @@ for seed in range(lo, hi):
             for k in lv:
                 if k not in ("reg", "cor"):
                     lv[k] = torch.round(lv[k] / quant) * quant
-    fused = lp.detect_postprocess(levels, (8, 16, 32), conf, iou, max_det)
+    half = bool(rng.integers(0, 2))   # fp16 level tensors: fused path on the halves, unfused chain on the upcast copy
+    if half:
+        h16 = [{k: v.half() for k, v in lv.items()} for lv in levels]
+        levels = [{k: v.float() for k, v in lv.items()} for lv in h16]
+    fused = lp.detect_postprocess(h16 if half else levels, (8, 16, 32), conf, iou, max_det)
     unfused = lp.non_max_suppression(lp.detect_decode(levels, (8, 16, 32)), conf, iou, max_det=max_det)
     for b, (f, u) in enumerate(zip(fused, unfused)):
         if not torch.equal(f, u):
             bad += 1
-            print(f"MISMATCH seed {seed} image {b}: B{B} {H}x{W} conf{conf} iou{iou} md{max_det} q{quant}")
+            print(f"MISMATCH seed {seed} image {b}: B{B} {H}x{W} conf{conf} iou{iou} md{max_det} q{quant} half{half}")
 print(f"seeds {lo}..{hi - 1}: {bad} mismatching images")
 sys.exit(1 if bad else 0)
