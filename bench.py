@@ -288,9 +288,28 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     torch.cuda.synchronize(dev)
     t_pipe = a.elapsed_time(b) / K
     dec_bytes, kf_bytes = B * A * (289 + 290) * 4, B * A * 277 * 4
+    # the same fused path on fp16 level tensors (model.half()): lp_detect_postprocess_f16 / _pipelined_f16
+    half_levels = [{k: v.half() for k, v in lv.items()} for lv in levels]
     del dec, plans, pipe, levels
+    plans = [PostprocessPlan(half_levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
+    fused_half = None
+    if plans[0].half:
+        t_serial_h = timed(lambda: plans[0].run(conf, iou))
+        pipe = PostprocessPipeline(plans)
+        burst()
+        torch.cuda.synchronize(dev)
+        a.record()
+        burst()
+        b.record()
+        torch.cuda.synchronize(dev)
+        fused_half = {"what": "the fused path on fp16 level tensors (lp_detect_postprocess_f16): exact upcast on load",
+                      "serial_ms_per_step": t_serial_h, "pipelined_ms_per_step": a.elapsed_time(b) / K,
+                      "images_per_s_pipelined": B / (a.elapsed_time(b) / K) * 1e3}
+        del pipe
+    del plans, half_levels
     torch.cuda.empty_cache()
     return {
+        "fused_path_half_levels": fused_half,
         "decode_kernel": {"kernel": "lp::decode_tma_kernel", "ms": t_dec, "algorithmic_bytes": dec_bytes,
                           "achieved_gbs": dec_bytes / t_dec / 1e6, "frac_of_hbm_peak": dec_bytes / t_dec / 1e6 / peak},
         "fused_path": {"what": "raw level tensors -> detections (lp_detect_postprocess_f32), no [B,A,290] tensor",
