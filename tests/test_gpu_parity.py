@@ -663,6 +663,52 @@ def test_fused_path_on_half_level_tensors_equals_f32_path_on_the_upcast_tensors(
         assert torch.equal(out[b, :k], ref_out[b, :k]), f"pipelined image {b}"
 
 
+@pytest.mark.parametrize("half", [False, True])
+def test_fused_path_with_foreign_kernels_sharing_the_sms(half):
+    """Small foreign kernels on another stream move onto the SMs beside the persistent KF CTAs and
+    perturb the relative speed of its warps.  That exposed an mbarrier phase-parity aliasing in an
+    earlier producer / finisher assignment (a waiter two phases ahead passes try_wait.parity): wrong
+    slots were overwritten and K2 then read garbage keys -- a launch failure after a few hundred runs.
+    Every run's result is compared on the device with the first one."""
+    from yolo_lp_b200.head import PostprocessPlan
+    levels = synth.synth_levels(32, 640, 640, DEV, seed=1)
+    if half:
+        levels = [{k: v.half() for k, v in lv.items()} for lv in levels]
+    plan = PostprocessPlan(levels, (8, 16, 32), 300)
+    out, counts = plan.run(0.25, 0.45)
+    ref_out, ref_counts = out.clone(), counts.clone()
+    side = torch.cuda.Stream(DEV)
+    rc = torch.randint(0, 300, (32,), device=DEV, dtype=torch.int32)
+    live = torch.arange(300, device=DEV)[None, :, None] < ref_counts[:, None, None]
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    torch.cuda.synchronize()
+    for _ in range(1500):
+        out, counts = plan.run(0.25, 0.45)
+        bad.add_(((out != ref_out) & live).any().long() + (counts != ref_counts).any().long())
+        with torch.cuda.stream(side):
+            _ = torch.arange(300, device=DEV)[None, :, None] < rc[:, None, None]
+    torch.cuda.synchronize()
+    assert int(bad) == 0
+
+
+def test_decode_with_foreign_kernels_sharing_the_sms():
+    """Same perturbation for the warp-specialised decode kernel (rings, named barriers, release warp)."""
+    levels = synth.synth_levels(16, 640, 640, DEV, seed=2)
+    plan = lp.DecodePlan(levels, (8, 16, 32))
+    ref = plan.run().clone()
+    side = torch.cuda.Stream(DEV)
+    rc = torch.randint(0, 300, (32,), device=DEV, dtype=torch.int32)
+    bad = torch.zeros((), dtype=torch.int64, device=DEV)
+    torch.cuda.synchronize()
+    for _ in range(600):
+        out = plan.run()
+        bad.add_((out.view(torch.int32) != ref.view(torch.int32)).any().long())
+        with torch.cuda.stream(side):
+            _ = torch.arange(300, device=DEV)[None, :, None] < rc[:, None, None]
+    torch.cuda.synchronize()
+    assert int(bad) == 0
+
+
 def test_heavy_suppression_walks_many_segments():
     """Few tight clusters, every anchor a candidate: far fewer than max_det boxes survive, so the
     greedy walk has to consume every score segment (and every window) of the 8400 candidates."""

@@ -11,7 +11,7 @@ dev = torch.device("cuda:0")
 levels = synth.synth_levels(B, img, img, dev, seed=0)
 plan = PostprocessPlan(levels, (8, 16, 32), 300)
 for _ in range(3): plan.run_filter(conf)
-buf = torch.zeros((148, 24, 4), dtype=torch.int64, device=dev)
+buf = torch.zeros((148, 23, 4), dtype=torch.int64, device=dev)
 _abi.call("lp_debug_nms_timing", buf.data_ptr())
 plan.run_filter(conf); torch.cuda.synchronize()
 _abi.call("lp_debug_nms_timing", None)
@@ -20,5 +20,5 @@ tiles = B * sum((h * w + 31) // 32 for h, w in synth.level_shapes(img, img)) / u
 print("CTAs", used.shape[0], "tiles/CTA %.1f" % tiles, "total cycles/tile/CTA %.0f" % (used[:, 0].sum(1).mean() / tiles))
 m = used.mean(0) / tiles
 print("scanner (per tile): other %.0f wait-full %.0f scan %.0f" % tuple(m[2, :3].tolist()))
-print("finisher (per own tile): other %.0f wait-bar %.0f finish %.0f" % tuple((m[16, :3] * 6).tolist()))
-print("producer (per own tile): other %.0f wait-empty %.0f issue %.0f" % tuple((m[22, :3] * 2).tolist()))
+print("finisher (per own tile): other %.0f wait-bar %.0f finish %.0f" % tuple((m[16, :3] * 5).tolist()))
+print("producer (per own tile): other %.0f wait-empty %.0f issue %.0f" % tuple((m[21, :3] * 5 / 3).tolist()))

@@ -6,7 +6,7 @@
 // reads of the survivors) all sit in one instruction stream.  Here they are three concurrent roles of
 // one persistent CTA per SM, over tiles of 32 positions ([277 class channels][32] = 35,456 B) in a
 // five-deep shared-memory ring:
-//   warps 22-23, lane 0  producers (tiles alternate between them): eight 3-D TMA box loads per tile
+//   warps 21-22, lane 0  producers (each owns alternate ring slots): eight 3-D TMA box loads per tile
 //                        (UTMALDG.3D, one per class tensor: all its channels x 32 positions of image
 //                        b), completion on the slot's `full` mbarrier, reuse gated by `empty`.  A
 //                        thread needs ~100 cycles per UTMALDG, hence two issuers;
@@ -18,15 +18,17 @@
 //                        named barrier -- scanners only ever wait for data.  (Eight scanners, one
 //                        whole group each, needed ~1100 cycles per tile -- a dependent-issue-bound
 //                        instruction stream -- against a ~1300-cycle HBM budget: too close.)
-//   warps 16-21          finishers, tile t belongs to finisher t % 6: wait until the slot's previous
-//                        tile has been taken over (its `empty` phase), bar.sync on the slot's barrier,
-//                        merge the two halves of every group, release the slot, one sigmoid of the
-//                        maximum per group (fused.cu explains why that is exact) plus one for the tie
-//                        test, then finish_tile (threshold, slot claim, key, the survivors' finished
-//                        rows): its global round trips (~2000 cycles) are off everybody else's path.
-//                        (The ordering on `empty` matters: with a free rotation a fast finisher's
-//                        bar.sync completed on the scanner arrivals of the slot's PREVIOUS tile, whose
-//                        own finisher was slow -- seen only on a cold workspace.)
+//   warps 16-20          finishers, one per ring slot: bar.sync on the slot's barrier, merge the two
+//                        halves of every group, release the slot, one sigmoid of the maximum per
+//                        group (fused.cu explains why that is exact) plus one for the tie test, then
+//                        finish_tile (threshold, slot claim, key, the survivors' finished rows): its
+//                        global round trips (~2000 cycles) are off everybody else's path.
+// Ownership is by SLOT everywhere (producer q: slots with s % 2 == q; finisher f: slot f), so every
+// waiter on a slot's mbarrier phase has itself seen the previous phase.  Two earlier assignments by
+// TILE were wrong in ways only a perturbed schedule shows (a cold workspace; foreign kernels sharing
+// the SMs, tools/pipeline_stress.py): a free finisher rotation let a fast finisher's bar.sync complete on
+// the scanner arrivals of the slot's previous tile, and with phase waits added, a waiter two phases
+// ahead passed mbarrier.try_wait.parity (which only distinguishes odd from even phases).
 // Tiles are assigned statically (tile = blockIdx.x + it * gridDim.x): every tile costs the same here.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
 #include <type_traits>
@@ -37,8 +39,8 @@ namespace lp {
 
 constexpr int KT_RING = 5;
 constexpr int KT_SCANNERS = 2 * NGROUP;              // warps 0..15: warp w scans half (w & 1) of group w >> 1
-constexpr int KT_FINISHERS = 6;                      // warps 16..21: tile t belongs to finisher t % 6
-constexpr int KT_PRODUCERS = 2;                      // warps 22..23
+constexpr int KT_FINISHERS = KT_RING;                // warps 16..20: finisher f owns ring slot f
+constexpr int KT_PRODUCERS = 2;                      // warps 21..22: producer q owns the slots with s % 2 == q
 constexpr int KT_THREADS = (KT_SCANNERS + KT_FINISHERS + KT_PRODUCERS) * 32;
 constexpr int KT_STAGE_ELEMS = (ROW - 13) * DEC_TILE;    // class planes only; 4 (2) bytes each
 constexpr int KT_STAGE_FLOATS = KT_STAGE_ELEMS;
@@ -136,7 +138,7 @@ __device__ __forceinline__ void locate(const LevelsFilterParams& p, int tile, in
 #ifdef LP_KF_PROFILE
 #define LP_PF_DECL long long pf[4] = {0, 0, 0, 0}, pf_t = clock64()
 #define LP_PF(k) do { const long long t1_ = clock64(); pf[k] += t1_ - pf_t; pf_t = t1_; } while (0)
-#define LP_PF_OUT() do { if (p.timing != nullptr && lane == 0) for (int k = 0; k < 4; ++k) p.timing[(blockIdx.x * 24 + warp) * 4 + k] = pf[k]; } while (0)
+#define LP_PF_OUT() do { if (p.timing != nullptr && lane == 0) for (int k = 0; k < 4; ++k) p.timing[(blockIdx.x * 23 + warp) * 4 + k] = pf[k]; } while (0)
 #else
 #define LP_PF_DECL do { } while (0)
 #define LP_PF(k) do { } while (0)
@@ -172,8 +174,13 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
     if (warp >= KT_SCANNERS + KT_FINISHERS) {            // ---- producers
         if (lane != 0) return;
         LP_PF_DECL;
-        for (int it = warp - (KT_SCANNERS + KT_FINISHERS); it < n_my; it += KT_PRODUCERS) {
+        // A producer owns whole ring slots, not alternate tiles: whoever waits on a slot's `empty` phase u
+        // must have seen phase u-1 itself, or try_wait's parity test mistakes "two phases behind" for
+        // "done" (the slot's previous tile not even taken over yet) and the stage is overwritten early.
+        const int q = warp - (KT_SCANNERS + KT_FINISHERS);
+        for (int it = 0; it < n_my; ++it) {
             const int s = it % KT_RING, use = it / KT_RING;
+            if (s % KT_PRODUCERS != q) continue;
             int b, l, p0;
             locate(p, first + it * step, b, l, p0);
             LP_PF(0);
@@ -190,18 +197,16 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
         LP_PF_OUT();
     } else if (warp >= KT_SCANNERS) {                    // ---- finishers
         LP_PF_DECL;
-        for (int it = warp - KT_SCANNERS; it < n_my; it += KT_FINISHERS) {
+        for (int it = warp - KT_SCANNERS; it < n_my; it += KT_FINISHERS) {   // it % KT_RING == this finisher's slot
             const int s = it % KT_RING;
             int b, l, p0;
             locate(p, first + it * step, b, l, p0);
             const DecodeLevel& lv = p.lv[l];
             LP_PF(0);
-            // Not before the slot's previous tile has been taken over by ITS finisher: a bar.sync issued
-            // earlier would complete on the 512 scanner arrivals that belong to that tile.
-            if (it >= KT_RING) {
-                if (lane == 0) mbar_wait_relaxed(&empty[s], (it / KT_RING - 1) & 1);
-                __syncwarp();
-            }
+            // (One finisher per SLOT: its tiles reach it in order, so its bar.sync can never complete on
+            // the scanner arrivals of the slot's previous tile -- which a free rotation allowed, first
+            // through plain overtaking, then, with an `empty`-phase wait in front, through the parity
+            // aliasing described at the producers.)
             slot_wait(s);
             LP_PF(1);               // all sixteen half-group results of tile `it` are in the exchange buffer
             float c[NGROUP];
@@ -262,6 +267,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
 cudaError_t launch_levels_filter_tma(const LevelsFilterParams& p, const DecodeMaps& maps, int num_ctas, cudaStream_t stream) {
     static_assert(KT_SMEM <= 227 * 1024, "KF stages exceed shared memory");
     static_assert(KT_RING + 1 <= 16, "one named barrier per ring slot");
+    static_assert(KT_FINISHERS == KT_RING, "a slot's consecutive tiles must share their finisher");
     static bool configured[64] = {false}, configured_h[64] = {false};
     cudaError_t e = p.half_levels ? configure_smem_once(levels_filter_tma_kernel<true>, KT_SMEM, configured_h)
                                   : configure_smem_once(levels_filter_tma_kernel<false>, KT_SMEM, configured);
