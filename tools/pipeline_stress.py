@@ -20,6 +20,15 @@ cfg = synth.CONFIGS[cid]
 B, A, dev = min(cfg["B"], 32), cfg["A"], torch.device("cuda:0")
 conf, iou, md = cfg["conf"], cfg["iou"], cfg["max_det"]
 bad = torch.zeros((), dtype=torch.int64, device=dev)
+side = torch.cuda.Stream(dev)
+junk = torch.rand(1 << 22, device=dev)
+
+
+def perturb(i):
+    """Foreign work on a third stream: kernels of varying size that move onto whatever SMs are free."""
+    with torch.cuda.stream(side):
+        n = 1 << (10 + i % 13)
+        junk[:n].mul_(1.0001).add_(0.5)
 
 
 def mark(out, counts, ref):
@@ -39,6 +48,7 @@ for dtype in (() if os.environ.get("SKIP_NMS") else (torch.float32, torch.float1
     pipe.start()
     for i in range(N):
         slot, out, counts = pipe.submit(preds[i % 3], conf, iou)
+        perturb(i)
         # compare on the NMS stream, right behind this step's K2 and before the slot is reused
         with torch.cuda.stream(pipe.s_nms):
             mark(out, counts, refs[i % 3])
@@ -58,6 +68,7 @@ for half in (False, True):
     pipe.start()
     for i in range(N):
         slot, out, counts = pipe.submit(conf, iou)
+        perturb(i)
         with torch.cuda.stream(pipe.s_nms):
             mark(out, counts, refs[slot])
     pipe.finish()
