@@ -74,4 +74,14 @@ for half in (False, True):
     pipe.finish()
     torch.cuda.synchronize()
     print(f"PostprocessPipeline half={half}: {N} submissions, mismatching steps so far: {int(bad)}")
+# the warp-specialised decode kernel, same treatment
+from yolo_lp_b200.head import DecodePlan
+dec = DecodePlan(levels[0], (8, 16, 32))
+ref = dec.run().clone()
+for i in range(N):
+    out = dec.run()
+    bad.add_((out.view(torch.int32) != ref.view(torch.int32)).any().long())
+    perturb(i)
+torch.cuda.synchronize()
+print(f"decode: {N} launches, mismatching steps so far: {int(bad)}")
 sys.exit(1 if int(bad) else 0)
