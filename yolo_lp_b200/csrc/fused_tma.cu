@@ -29,6 +29,8 @@
 // the SMs, tools/pipeline_stress.py): a free finisher rotation let a fast finisher's bar.sync complete on
 // the scanner arrivals of the slot's previous tile, and with phase waits added, a waiter two phases
 // ahead passed mbarrier.try_wait.parity (which only distinguishes odd from even phases).
+// The kernel is instantiated for fp32 and for fp16 level tensors (kHalf: FLOAT16 tensor maps, 64-byte
+// stage rows with every group starting on an even row, exact upcast in the scanners and finishers).
 // Tiles are assigned statically (tile = blockIdx.x + it * gridDim.x): every tile costs the same here.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
 #include <type_traits>
