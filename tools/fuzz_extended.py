@@ -20,8 +20,9 @@ bad = 0
 for seed in range(lo, hi):
     rng = np.random.default_rng(seed)
     B = int(rng.integers(1, 5))
-    A = int(rng.choice([33, 315, 2100, 5040, 8400, 12000]))
-    n_pos = int(rng.integers(0, min(A, 3000)))
+    big = os.environ.get("BIG") == "1"     # BIG=1: 1280x1280-sized inputs, thousands of candidates
+    A = int(rng.choice([8400, 16000, 33600] if big else [33, 315, 2100, 5040, 8400, 12000]))
+    n_pos = int(rng.integers(0, min(A, 9000 if big else 3000)))
     conf = float(rng.choice([0.0, 0.01, 0.05, 0.25, 0.6]))
     iou = float(rng.choice([0.0, 0.2, 0.45, 0.65, 1.0]))
     max_det = int(rng.choice([1, 7, 64, 300, 1000]))
