@@ -20,6 +20,10 @@
  *   lp_detect_postprocess_f32 <- effidehead.py:247-301 + nms.py:31-130 fused (no head tensor)
  *   lp_txt_records_f32 / lp_txt_lines_host <- yolov6/core/inferer.py:92-93,103-120 (--save-txt records)
  *   lp_eval_match_f32 / lp_eval_accumulate_host <- yolov6/core/evaler.py:153-283 (LP metric)
+ *   lp_prepare_targets_f32   <- yolov6/core/evaler.py:119-127 (Evaler.predict label prep)
+ *   lp_nms_f16, lp_detect_postprocess_f16 (+ stage / pipelined twins)
+ *                            <- the same calls in the reference's --half mode
+ *                               (yolov6/core/inferer.py:46-50, evaler.py:116)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer on the current CUDA device unless the
