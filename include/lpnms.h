@@ -128,7 +128,7 @@ LP_API int lp_tune(int key, int value);
 LP_API int lp_debug_nms_timing(long long* buf);
 
 /*
- * One pipelined step driven from two streams of the caller (native equivalent of
+ * One pipelined step driven from (at least) two streams of the caller (native equivalent of
  * yolo_lp_b200.nms.NmsPipeline.submit): K1 on filter_stream, K2 on nms_stream, ordered by
  * filtered_event; workspace_free_event (may be NULL) is the done_event of the step that last used
  * this workspace; done_event / time_*_event (may be NULL) are recorded after K2 / round K1.
