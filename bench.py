@@ -430,8 +430,8 @@ def run_ours(args):
     # every TIME_EVERY-th K1 launch is bracketed by timing events.  A timed launch is fenced off from
     # its neighbours (consecutive K1s otherwise overlap each other's drain and ramp-up, and a bracket
     # would then measure queueing, not the kernel), which costs ~20 us of bubble per timed launch --
-    # so only about ten launches of the timed region are measured this way.
-    n_timed = max(1, min(10, K // 16))
+    # so only a handful of launches of the timed region (one per 32 steps, six at most) are measured this way.
+    n_timed = max(1, min(6, K // 32))
     TIME_EVERY = max(1, K // n_timed)
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in list(range(TIME_EVERY // 2, K, TIME_EVERY))[:n_timed]}   # never step 0: the pipeline is still filling
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -494,7 +494,7 @@ def run_ours(args):
                 "share_of_serial_step": lat_filter / (lat_filter + lat_nms),   # the figure an ncu launch list (serialised) shows
                 "timed_launches": len(filt_ms),
                 "note": "K1 timed inside the pipelined region, K2 of the previous step running concurrently; the timed launches "
-                        "(about ten per run) are fenced off from the neighbouring K1s, which otherwise overlap each other's drain and "
+                        "(one per 32 steps, six at most) are fenced off from the neighbouring K1s, which otherwise overlap each other's drain and "
                         "ramp-up -- hence share_of_step > 1"}
 
     # ---- end-to-end leg: public API on a pinned HOST tensor; H2D + kernels + D2H per step
