@@ -86,3 +86,26 @@ def test_product_never_imports_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
             assert "/root/reference" not in src, fn
+
+
+def test_ctypes_signatures_have_the_headers_parameter_counts(lib):
+    """ABI drift guard: every prototype in include/lpnms.h and its ctypes entry must agree on the
+    number of parameters (a missing / extra argument would otherwise only show as a crash)."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lpnms.h")).read(), flags=re.S)
+    protos = re.findall(r"LP_API\s+[\w\s\*]+?\b(lp_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(_abi.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([q for q in params.split(",") if q.strip()])
+        assert n == len(_abi.SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes table {len(_abi.SIGNATURES[name][1])}"
+
+
+def test_f16_entries_validate_like_the_f32_ones(lib):
+    for name in ("lp_nms_f16", "lp_nms_f32"):
+        f = getattr(lib, name)
+        assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None) == -1
+        buf = ctypes.create_string_buffer(1 << 16)
+        p = (ctypes.addressof(buf) + 255) // 256 * 256
+        assert f(p, 1, 8, 1.5, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -5
+        assert f(p + 8, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -3
+        assert f(p, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 16, p + 32768, p + 49152, None, None, 0, None) == -4
