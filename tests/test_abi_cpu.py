@@ -109,3 +109,31 @@ def test_f16_entries_validate_like_the_f32_ones(lib):
         assert f(p, 1, 8, 1.5, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -5
         assert f(p + 8, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -3
         assert f(p, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 16, p + 32768, p + 49152, None, None, 0, None) == -4
+
+
+def test_ctypes_argument_kinds_match_the_header(lib):
+    """... and on the KIND of every parameter: pointer, int, long long, size_t, float or double."""
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lpnms.h")).read(), flags=re.S)
+    protos = re.findall(r"LP_API\s+[\w\s\*]+?\b(lp_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+
+    def header_kind(decl):
+        d = " ".join(decl.split())
+        if "*" in d or "lp_stream_t" in d:
+            return "ptr"
+        for key, kind in (("size_t", "size_t"), ("long long", "longlong"), ("double", "double"), ("float", "float"), ("int", "int")):
+            if re.search(r"\b" + key + r"\b", d):
+                return kind
+        raise AssertionError(f"unparsed parameter {decl!r}")
+
+    def ctypes_kind(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or isinstance(t, type(ctypes.POINTER(ctypes.c_int))):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_double: "double", ctypes.c_float: "float", ctypes.c_size_t: "size_t",
+                ctypes.c_longlong: "longlong"}[t]
+
+    for name, params in protos:
+        decls = [q for q in params.split(",") if q.strip() and q.strip() != "void"]
+        want = [header_kind(d) for d in decls]
+        got = [ctypes_kind(t) for t in _abi.SIGNATURES[name][1]]
+        # size_t and c_size_t / c_ulong are the same thing on this ABI
+        assert got == want, f"{name}: header {want} vs ctypes {got}"
