@@ -30,7 +30,9 @@
  *     parameter name ends in _host;
  *   - the library never allocates, frees or synchronises; all work is queued on
  *     the cudaStream_t passed as `stream` (void* here so C callers need no CUDA
- *     headers); it keeps no global state and is re-entrant;
+ *     headers); it keeps no global state and is re-entrant: tuning / debug knobs
+ *     are a per-call `const lp_opts_t* opts` HOST pointer (NULL = defaults), the
+ *     last parameter of every entry that launches K1 / KF / K2 / decode;
  *   - every function returns int: 0 = ok, <0 = LP_E_* argument error,
  *     >0 = cudaError_t of a failed launch; nothing throws, aborts or exits.
  */
@@ -43,7 +45,7 @@
 extern "C" {
 #endif
 
-#define LP_VERSION 100            /* major*10000 + minor*100 + patch */
+#define LP_VERSION 200            /* major*10000 + minor*100 + patch */
 #define LP_ROW 290                /* floats per head row: 4 box | 1 obj | 8 corners | 31 | 24 | 6x37 */
 #define LP_OUT 28                 /* floats per detection: 4 xyxy | 8 corners | 8 conf | 8 argmax */
 #define LP_MAX_LEVELS 4
@@ -76,6 +78,16 @@ typedef struct lp_level {
     float stride;
 } lp_level_t;
 
+/* Per-call knobs; NULL or all-zero = production behaviour.  Results never depend on them. */
+typedef struct lp_opts {
+    int filter_ctas;     /* CTA count of K1 (lp::filter_kernel) / KF (lp::levels_filter_*); 0 = heuristic */
+    int no_tma;          /* != 0: the cp.async / register-resident kernels of the decode and fused paths
+                            instead of their TMA variants (same results) */
+    long long* timing;   /* debug: DEVICE buffer [B,16] of int64 that K2 fills with clock64() stamps of its
+                            phases (the decode / fused kernels of -DLP_DEC_PROFILE / -DLP_KF_PROFILE builds
+                            write per-role cycle sums to it); NULL = off */
+} lp_opts_t;
+
 LP_API int lp_version(void);
 LP_API const char* lp_error_string(int code);
 
@@ -100,7 +112,8 @@ LP_API int lp_nms_workspace_bytes(int B, int A, int max_det, size_t* out_bytes);
 LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres,
                int max_det, int max_nms, void* workspace, size_t workspace_bytes,
                float* out, int* counts, int* kept_anchor,
-               const float* rescale, int do_round, lp_stream_t stream);
+               const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 
 /*
  * The two stages of lp_nms_f32, separately launchable (profiling, per-stage timing):
@@ -111,21 +124,12 @@ LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double
  * lp_nms_f32 == lp_nms_filter_f32 followed by lp_nms_suppress_f32 on the same stream.
  */
 LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
-                             size_t workspace_bytes, lp_stream_t stream);
+                             size_t workspace_bytes, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
                                void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                               const float* rescale, int do_round, lp_stream_t stream);
-
-/* Tuning (process-global, not thread-safe): key 0 = the CTA count of K1 / KF (0 = default
- * heuristic); key 1 = 0 forces the cp.async / register-resident kernels of the decode and fused
- * paths instead of their TMA variants (same results; 1 = default, TMA when the shapes allow). */
-LP_API int lp_tune(int key, int value);
-
-/* Debug only (process-global, not thread-safe): device buffer [B,16] of int64 that K2 fills with
- * clock64() stamps at its phase boundaries (tools/nms_phase_timing.py; the decode / fused kernels of
- * -DLP_DEC_PROFILE / -DLP_KF_PROFILE builds write their per-role cycle sums to it too); NULL
- * switches it off. */
-LP_API int lp_debug_nms_timing(long long* buf);
+                               const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 
 /*
  * One pipelined step driven from (at least) two streams of the caller (native equivalent of
@@ -139,14 +143,17 @@ LP_API int lp_debug_nms_timing(long long* buf);
  * overlap (cfg2: 48.2 -> 44.5 us per step); yolo_lp_b200.nms.NmsPipeline does this.
  * K2 of a pipelined step zeroes the workspace's candidate counters once it has read them; a
  * non-NULL workspace_free_event therefore also asserts that the LAST operation on this workspace
- * was such a step, and lets the entry skip the memset node in front of K1.  Pass NULL whenever the
- * workspace is fresh or was last touched by any other entry point.
+ * was such a step WITH THE SAME B, and lets the entry skip the memset node in front of K1.  Pass
+ * NULL whenever the workspace is fresh, was last touched by any other entry point, is used with a
+ * different B, or the previous step on it returned an error.  Every argument of both stages is
+ * validated before anything is queued, so a failing call leaves the workspace as it was.
  */
 LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
                                 int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                 int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
                                 lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                void* done_event, void* time_begin_event, void* time_end_event);
+                                void* done_event, void* time_begin_event, void* time_end_event,
+        const lp_opts_t* opts);
 
 /*
  * fp16 head tensors (the reference's --half mode: inferer.py:46-50, evaler.py:116; SURVEY §8-f rank
@@ -158,17 +165,21 @@ LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thr
  */
 LP_API int lp_nms_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
                       void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                      const float* rescale, int do_round, lp_stream_t stream);
+                      const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_nms_filter_f16(const void* pred, int B, int A, double conf_thres, void* workspace,
-                             size_t workspace_bytes, lp_stream_t stream);
+                             size_t workspace_bytes, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_nms_suppress_f16(const void* pred, int B, int A, double iou_thres, int max_det, int max_nms,
                                void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                               const float* rescale, int do_round, lp_stream_t stream);
+                               const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_nms_pipelined_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
                                 int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                 int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
                                 lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                void* done_event, void* time_begin_event, void* time_end_event);
+                                void* done_event, void* time_begin_event, void* time_end_event,
+        const lp_opts_t* opts);
 
 /* Debug / property tests: the decode kernel's sigmoid evaluated on a flat device array. */
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream);
@@ -176,7 +187,8 @@ LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_str
 /* Detect.forward eval tail: raw per-level conv outputs -> out[B,A,290],
  * A = sum h*w, levels in order; anchors are computed from the index, never
  * materialised. */
-LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int B, float* out, lp_stream_t stream);
+LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int B, float* out, lp_stream_t stream,
+        const lp_opts_t* opts);
 
 /*
  * Fused head tail + NMS: raw per-level conv outputs -> detections, without materialising the
@@ -189,12 +201,15 @@ LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_byte
 LP_API int lp_detect_postprocess_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
                                      double iou_thres, int max_det, int max_nms, void* workspace,
                                      size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                                     const float* rescale, int do_round, lp_stream_t stream);
+                                     const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_detect_filter_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres, int max_det,
-                                void* workspace, size_t workspace_bytes, lp_stream_t stream);
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_detect_suppress_f32(const lp_level_t* levels_host, int n_levels, int B, double iou_thres, int max_det,
                                   int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream);
+                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 
 /* lp_nms_pipelined_f32 for the fused path: KF on filter_stream, K2 on nms_stream. */
 LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
@@ -202,7 +217,8 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, 
                                    size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                    const float* rescale, int do_round, lp_stream_t filter_stream,
                                    lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                   void* done_event, void* time_begin_event, void* time_end_event);
+                                   void* done_event, void* time_begin_event, void* time_end_event,
+        const lp_opts_t* opts);
 
 /*
  * The fused path on fp16 level tensors (model.half(): the prediction convs emit halves).  The
@@ -214,15 +230,18 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, 
 LP_API int lp_detect_postprocess_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
                                      double iou_thres, int max_det, int max_nms, void* workspace,
                                      size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                                     const float* rescale, int do_round, lp_stream_t stream);
+                                     const float* rescale, int do_round, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_detect_filter_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres, int max_det,
-                                void* workspace, size_t workspace_bytes, lp_stream_t stream);
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream,
+        const lp_opts_t* opts);
 LP_API int lp_detect_pipelined_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
                                    double iou_thres, int max_det, int max_nms, void* workspace,
                                    size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
                                    const float* rescale, int do_round, lp_stream_t filter_stream,
                                    lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                   void* done_event, void* time_begin_event, void* time_end_event);
+                                   void* done_event, void* time_begin_event, void* time_end_event,
+        const lp_opts_t* opts);
 
 /* generate_anchors(is_eval=True, mode='af'): anchor_points[A,2], stride_tensor[A]. */
 LP_API int lp_generate_anchors_f32(const int* h_host, const int* w_host, const float* stride_host, int n_levels,

@@ -32,7 +32,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.lp_version() == 100
+    assert lib.lp_version() == 200
     assert lib.lp_error_string(0) == b"ok"
     assert b"threshold" in lib.lp_error_string(-5)
     assert b"workspace" in lib.lp_error_string(-4)
@@ -53,20 +53,20 @@ def test_workspace_query(lib):
 def test_argument_validation_without_gpu(lib):
     # every check below is rejected before any CUDA call is made
     f = lib.lp_nms_f32
-    assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None) == -1
+    assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None, None) == -1
     buf = ctypes.create_string_buffer(1 << 16)
     base = ctypes.addressof(buf)
     p = (base + 255) // 256 * 256
     args = dict(pred=p, ws=p + 4096, out=p + 32768, counts=p + 49152)
-    assert f(args["pred"], 1, 8, 1.5, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -5
-    assert f(args["pred"], 1, 8, 0.25, -0.1, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -5
-    assert f(args["pred"] + 8, 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -3
-    assert f(args["pred"], 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 16, args["out"], args["counts"], None, None, 0, None) == -4
-    assert f(args["pred"], 0, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None) == -2
+    assert f(args["pred"], 1, 8, 1.5, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None, None) == -5
+    assert f(args["pred"], 1, 8, 0.25, -0.1, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None, None) == -5
+    assert f(args["pred"] + 8, 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None, None) == -3
+    assert f(args["pred"], 1, 8, 0.25, 0.45, 300, 30000, args["ws"], 16, args["out"], args["counts"], None, None, 0, None, None) == -4
+    assert f(args["pred"], 0, 8, 0.25, 0.45, 300, 30000, args["ws"], 1 << 30, args["out"], args["counts"], None, None, 0, None, None) == -2
     assert lib.lp_rescale_f32(p, 4, 8, 0.0, 0.0, 1.0, 10.0, 10.0, 0, None) == -2     # row stride < 12
     assert lib.lp_rescale_f32(p, 4, 12, 0.0, 0.0, 0.0, 10.0, 10.0, 0, None) == -6    # ratio must be > 0
     assert lib.lp_dist2bbox_f32(p + 4, p, 1, 8, 0, p, None) == -3
-    assert lib.lp_detect_decode_f32(None, 3, 1, p, None) == -1
+    assert lib.lp_detect_decode_f32(None, 3, 1, p, None, None) == -1
 
 
 def test_check_maps_errors_like_the_reference(lib):
@@ -103,12 +103,12 @@ def test_ctypes_signatures_have_the_headers_parameter_counts(lib):
 def test_f16_entries_validate_like_the_f32_ones(lib):
     for name in ("lp_nms_f16", "lp_nms_f32"):
         f = getattr(lib, name)
-        assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None) == -1
+        assert f(None, 1, 8, 0.25, 0.45, 300, 30000, None, 0, None, None, None, None, 0, None, None) == -1
         buf = ctypes.create_string_buffer(1 << 16)
         p = (ctypes.addressof(buf) + 255) // 256 * 256
-        assert f(p, 1, 8, 1.5, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -5
-        assert f(p + 8, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None) == -3
-        assert f(p, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 16, p + 32768, p + 49152, None, None, 0, None) == -4
+        assert f(p, 1, 8, 1.5, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None, None) == -5
+        assert f(p + 8, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 1 << 30, p + 32768, p + 49152, None, None, 0, None, None) == -3
+        assert f(p, 1, 8, 0.25, 0.45, 300, 30000, p + 4096, 16, p + 32768, p + 49152, None, None, 0, None, None) == -4
 
 
 def test_ctypes_argument_kinds_match_the_header(lib):
@@ -137,3 +137,52 @@ def test_ctypes_argument_kinds_match_the_header(lib):
         got = [ctypes_kind(t) for t in _abi.SIGNATURES[name][1]]
         # size_t and c_size_t / c_ulong are the same thing on this ABI
         assert got == want, f"{name}: header {want} vs ctypes {got}"
+
+
+def test_pipelined_entries_validate_before_queueing(lib):
+    """lp_nms_pipelined_* / lp_detect_pipelined_* must reject every bad K2 argument before
+    K1 / KF is queued (a half-queued step would leave the workspace counters dirty).  Without a GPU the
+    proof is that the error comes back as an LP_E_* code, not as a CUDA error from a stream call."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    p = (ctypes.addressof(buf) + 255) // 256 * 256
+    ev = 1  # a non-NULL event handle; never dereferenced because validation fails first
+    for name in ("lp_nms_pipelined_f32", "lp_nms_pipelined_f16"):
+        f = getattr(lib, name)
+        ok = dict(pred=p, B=1, A=8, conf=0.25, iou=0.45, max_det=300, max_nms=30000, ws=p + 4096, ws_bytes=1 << 30,
+                  out=p + 32768, counts=p + 49152)
+
+        def call(**kw):
+            a = dict(ok, **kw)
+            return f(a["pred"], a["B"], a["A"], a["conf"], a["iou"], a["max_det"], a["max_nms"], a["ws"], a["ws_bytes"],
+                     a["out"], a["counts"], None, None, 0, None, None, None, ev, None, None, None, None)
+        assert call(counts=None) == -1          # K2 argument
+        assert call(out=None) == -1
+        assert call(max_nms=0) == -2
+        assert call(iou=1.5) == -5
+        assert call(conf=-0.5) == -5
+        assert call(ws_bytes=64) == -4
+        assert call(pred=p + 8) == -3
+    lv = (_abi.LpLevel * 1)()
+    for g in range(8):
+        lv[0].cls[g] = p
+    lv[0].reg, lv[0].cor, lv[0].h, lv[0].w, lv[0].stride = p, p, 2, 4, 8.0
+    for name in ("lp_detect_pipelined_f32", "lp_detect_pipelined_f16"):
+        f = getattr(lib, name)
+
+        def call(iou=0.45, max_nms=30000, counts=p + 49152, ws_bytes=1 << 30):
+            return f(lv, 1, 1, 0.25, iou, 300, max_nms, p + 4096, ws_bytes, p + 32768, counts, None, None, 0, None, None,
+                     None, ev, None, None, None, None)
+        assert call(counts=None) == -1
+        assert call(max_nms=0) == -2
+        assert call(iou=2.0) == -5
+        assert call(ws_bytes=64) == -4
+
+
+def test_opts_struct_matches_the_header():
+    text = open(os.path.join(ROOT, "include", "lpnms.h")).read()
+    body = re.search(r"typedef struct lp_opts \{(.*?)\} lp_opts_t;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [d.split()[-1].lstrip("*") for d in body.split(";") if d.strip()]
+    assert fields == [n for n, _ in _abi.LpOpts._fields_]
+    o = _abi.opts(filter_ctas=7, no_tma=True, timing=4096)
+    assert (o.filter_ctas, o.no_tma, o.timing) == (7, 1, 4096)

@@ -289,16 +289,14 @@ def test_decode_full_size_vs_oracle():
 @pytest.mark.parametrize("B,H,W", [(32, 640, 640), (3, 1280, 1280), (5, 416, 640), (1, 64, 96), (2, 608, 608)])
 def test_decode_tma_path_equals_lsu_path_and_repeats(B, H, W):
     """The warp-specialised TMA kernel (decode_tma.cu) and the cp.async kernel (decode.cu, forced with
-    lp_tune(1, 0)) share the arithmetic: bit-identical outputs; 20 repeats of the TMA kernel over a
+    the per-call knob lp_opts_t.no_tma) share the arithmetic: bit-identical outputs; 20 repeats of the TMA kernel over a
     poisoned output catch ring / barrier races.  608x608 has a 19x19 level (rows not 16-byte aligned):
     both settings then run the 4-byte cp.async path."""
     from yolo_lp_b200 import _abi
     levels = synth.synth_levels(B, H, W, DEV, seed=B + H)
-    try:
-        _abi.call("lp_tune", 1, 0)
-        ref = lp.detect_decode(levels, (8, 16, 32)).clone()
-    finally:
-        _abi.call("lp_tune", 1, 1)
+    lsu = lp.DecodePlan(levels, (8, 16, 32))
+    lsu.opts = _abi.opts(no_tma=True)
+    ref = lsu.run().clone()
     plan = lp.DecodePlan(levels, (8, 16, 32))
     for _ in range(20):
         plan.out.fill_(float("nan"))
@@ -312,17 +310,14 @@ def test_fused_tma_path_equals_lsu_path_many_tiles_per_cta(B, H, W, conf):
     producer / scanner / finisher hand-offs of fused_tma.cu all wrap many times.  First run on a
     poisoned workspace (a cold workspace makes the finishers slow -- that once let a fast finisher
     take over a barrier that belonged to a slow one), then back-to-back repeats; reference = the
-    register-resident kernel of fused.cu (forced with lp_tune(1, 0)), itself pinned to
+    register-resident kernel of fused.cu (forced with lp_opts_t.no_tma), itself pinned to
     decode -> K1 -> K2 by test_fused_postprocess_equals_decode_then_nms."""
     from yolo_lp_b200 import _abi
     levels = synth.synth_levels(B, H, W, DEV, seed=7)
-    try:
-        _abi.call("lp_tune", 1, 0)
-        ref = lp.PostprocessPlan(levels, (8, 16, 32), 300)
-        ref_out, ref_counts = ref.run(conf, 0.45)
-        torch.cuda.synchronize()
-    finally:
-        _abi.call("lp_tune", 1, 1)
+    ref = lp.PostprocessPlan(levels, (8, 16, 32), 300)
+    ref.opts = _abi.opts(no_tma=True)
+    ref_out, ref_counts = ref.run(conf, 0.45)
+    torch.cuda.synchronize()
 
     def same(out, counts):
         return torch.equal(counts, ref_counts) and all(
@@ -419,14 +414,12 @@ def test_filter_cta_limit_does_not_change_results():
     pred = synth.synth_head(3, 8400, 640, 24, 300, seed=61)
     want = lp_oracle.non_max_suppression(pred.numpy(), 0.25, 0.45)
     dev = pred.to(DEV)
-    try:
-        for ctas in (1, 7, 148, 0):
-            _abi.call("lp_tune", 0, ctas)
-            got = lp.non_max_suppression(dev, 0.25, 0.45)
-            for b in range(3):
-                assert_rows_equal(got[b].cpu().numpy(), want[b], f"ctas={ctas}[{b}]")
-    finally:
-        _abi.call("lp_tune", 0, 0)
+    plan = lp.NmsPlan(3, 8400, 300, DEV)
+    for ctas in (1, 7, 148, 0):
+        plan.opts = _abi.opts(filter_ctas=ctas)
+        out, counts = plan.run(dev, 0.25, 0.45)
+        for b, k in enumerate(counts.cpu().tolist()):
+            assert_rows_equal(out[b, :k].cpu().numpy(), want[b], f"ctas={ctas}[{b}]")
 
 
 # ------------------------------------------------------------------ fused raw-levels -> detections

@@ -25,9 +25,9 @@ A = sum(h * w for h, w in synth.level_shapes(img, img))
 out = torch.empty((B, A, 290), device=dev)
 from yolo_lp_b200 import _abi
 from yolo_lp_b200.head import DecodePlan
-if os.environ.get("DEC_TMA") == "0":
-    _abi.call("lp_tune", 1, 0)     # force the cp.async load path
 plan = DecodePlan(levels, (8, 16, 32), out)
+if os.environ.get("DEC_TMA") == "0":
+    plan.opts = _abi.opts(no_tma=True)     # force the cp.async load path
 for _ in range(5):
     plan.run()
 torch.cuda.synchronize()
@@ -47,10 +47,9 @@ except Exception:
     pass
 if os.environ.get("DEC_PROFILE"):   # library built with LPNMS_NVCC_EXTRA=-DLP_DEC_PROFILE
     buf = torch.zeros((148, 3, 4), dtype=torch.int64, device=dev)
-    _abi.call("lp_debug_nms_timing", buf.data_ptr())
+    plan.opts = _abi.opts(no_tma=os.environ.get("DEC_TMA") == "0", timing=buf.data_ptr())
     plan.run()
     torch.cuda.synchronize()
-    _abi.call("lp_debug_nms_timing", None)
     tiles = B * sum((h * w + 31) // 32 for h, w in synth.level_shapes(img, img)) / 148
     t = (buf.double().mean(0) / tiles).tolist()
     print("cycles per tile  load producer: other %.0f wait-empty %.0f issue %.0f" % tuple(t[0][:3]))

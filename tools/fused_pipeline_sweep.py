@@ -35,8 +35,9 @@ def timed(fn, k=K):
 
 
 for ctas in CTAS:
-    _abi.call("lp_tune", 0, ctas)
     plans = [PostprocessPlan(levels, (8, 16, 32), 300) for _ in range(2)]
+    for pl in plans:
+        pl.opts = _abi.opts(filter_ctas=ctas)
     t_kf = timed(lambda: plans[0].run_filter(conf))
     t_s = timed(lambda: plans[0].run(conf, iou))
     pipe = PostprocessPipeline(plans)
@@ -48,4 +49,3 @@ for ctas in CTAS:
         pipe.finish()
     t_p = timed(burst, 3) / K
     print(f"KF ctas={ctas or 'auto':>4}: KF alone {t_kf:6.1f} us  serial step {t_s:6.1f} us  pipelined step {t_p:6.1f} us ({B / t_p * 1e6:8.0f} img/s)")
-_abi.call("lp_tune", 0, 0)

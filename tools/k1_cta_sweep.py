@@ -13,7 +13,7 @@ dev = torch.device("cuda:0")
 pred = torch.rand((B, A, 290), device=dev) * 0.1
 plan = NmsPlan(B, A, 300, dev)
 for ctas in (0, 148, 116, 100, 84, 74, 60, 48):
-    _abi.call("lp_tune", 0, ctas)
+    plan.opts = _abi.opts(filter_ctas=ctas)
     for _ in range(5):
         plan.run_filter(pred, 0.25)
     torch.cuda.synchronize()
@@ -25,4 +25,3 @@ for ctas in (0, 148, 116, 100, 84, 74, 60, 48):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 30
     print(f"K1 ctas={ctas or 'auto':>4}: {ms * 1e3:7.1f} us  {B * A * 1160 / ms / 1e6:7.0f} GB/s")
-_abi.call("lp_tune", 0, 0)

@@ -12,9 +12,9 @@ levels = synth.synth_levels(B, img, img, dev, seed=0)
 plan = PostprocessPlan(levels, (8, 16, 32), 300)
 for _ in range(3): plan.run_filter(conf)
 buf = torch.zeros((148, 23, 4), dtype=torch.int64, device=dev)
-_abi.call("lp_debug_nms_timing", buf.data_ptr())
+plan.opts = _abi.opts(timing=buf.data_ptr())
 plan.run_filter(conf); torch.cuda.synchronize()
-_abi.call("lp_debug_nms_timing", None)
+plan.opts = None
 used = buf[buf.sum((1, 2)) > 0].double()
 tiles = B * sum((h * w + 31) // 32 for h, w in synth.level_shapes(img, img)) / used.shape[0]
 print("CTAs", used.shape[0], "tiles/CTA %.1f" % tiles, "total cycles/tile/CTA %.0f" % (used[:, 0].sum(1).mean() / tiles))

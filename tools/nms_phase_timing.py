@@ -20,10 +20,10 @@ plan = NmsPlan(B, cfg["A"], cfg["max_det"], dev)
 buf = torch.zeros((B, 16), dtype=torch.int64, device=dev)
 for _ in range(3):
     plan.run(pred, cfg["conf"], cfg["iou"])
-_abi.call("lp_debug_nms_timing", buf.data_ptr())
+plan.opts = _abi.opts(timing=buf.data_ptr())
 plan.run(pred, cfg["conf"], cfg["iou"])
 torch.cuda.synchronize()
-_abi.call("lp_debug_nms_timing", None)
+plan.opts = None
 t = buf.cpu()
 names = ["order (sort / histogram)", "first segment + window", "nms", "gather"]
 d = torch.stack([t[:, 2] - t[:, 0], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4]], 1).double()

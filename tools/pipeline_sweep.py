@@ -31,10 +31,12 @@ def timed(fn, k=K):
 
 
 for ctas in (0, 148, 132, 116, 100, 84):
-    _abi.call("lp_tune", 0, ctas)
+    plan.opts = _abi.opts(filter_ctas=ctas)
     t_f = timed(lambda: plan.run_filter(pred, cfg["conf"]))
     t_s = timed(lambda: plan.run(pred, cfg["conf"], cfg["iou"]))
     pipe = NmsPipeline(B, cfg["A"], cfg["max_det"], dev)
+    for pl in pipe.plans:
+        pl.opts = plan.opts
     ref = plan.counts.clone()
 
     def go():
@@ -53,4 +55,3 @@ for ctas in (0, 148, 132, 116, 100, 84):
     ok = all(torch.equal(p.counts, ref) for p in pipe.plans)
     print(f"cfg{cid} K1 ctas={ctas or 148:3d}: filter alone {t_f:7.1f} us  serial step {t_s:7.1f} us  pipelined step {t_p:7.1f} us"
           f"  ({B / t_p * 1e6:9.0f} img/s)  counts_ok={ok}")
-_abi.call("lp_tune", 0, 0)

@@ -27,46 +27,54 @@ class LpLevel(ctypes.Structure):
                 ("h", c_int), ("w", c_int), ("stride", c_float)]
 
 
+class LpOpts(ctypes.Structure):
+    """``lp_opts_t``: per-call tuning / debug knobs (NULL = production defaults)."""
+    _fields_ = [("filter_ctas", c_int), ("no_tma", c_int), ("timing", c_void_p)]
+
+
+def opts(filter_ctas: int = 0, no_tma: bool = False, timing: int | None = None) -> LpOpts:
+    """``timing``: device address of an int64 ``[B,16]`` buffer (``tensor.data_ptr()``)."""
+    return LpOpts(int(filter_ctas), int(bool(no_tma)), timing)
+
+
 #: name -> (restype, argtypes); must list every LP_API symbol of include/lpnms.h
 SIGNATURES = {
     "lp_version": (c_int, []),
     "lp_error_string": (c_char_p, [c_int]),
     "lp_nms_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "lp_nms_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_nms_pipelined_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lp_nms_filter_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_nms_filter_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p, POINTER(LpOpts)]),
     "lp_nms_suppress_f32": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_nms_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_nms_pipelined_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_double, c_int, c_int, c_void_p, c_size_t,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lp_nms_filter_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_nms_filter_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_void_p, c_size_t, c_void_p, POINTER(LpOpts)]),
     "lp_nms_suppress_f16": (c_int, [c_void_p, c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
-                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "lp_debug_nms_timing": (c_int, [c_void_p]),
-    "lp_tune": (c_int, [c_int, c_int]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_debug_sigmoid_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
-    "lp_detect_decode_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p]),
+    "lp_detect_decode_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p, POINTER(LpOpts)]),
     "lp_detect_postprocess_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
-                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_detect_pipelined_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
     "lp_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
-    "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p]),
+    "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p, POINTER(LpOpts)]),
     "lp_detect_postprocess_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
-                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                          c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_detect_pipelined_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lp_detect_filter_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_detect_filter_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p, POINTER(LpOpts)]),
     "lp_detect_suppress_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_int, c_void_p, c_size_t,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_generate_anchors_f32": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_float), c_int, c_float,
                                         c_void_p, c_void_p, c_void_p]),
     "lp_dist2bbox_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
@@ -82,6 +90,7 @@ SIGNATURES = {
     "lp_rescale_batch_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
 }
 
+_OPTS_PTR = POINTER(LpOpts)   # ctypes caches pointer types: this is the object the table above holds
 _lib = None
 
 
@@ -119,7 +128,10 @@ def check(fn: str, code: int) -> None:
     raise LpError(fn, code, text)
 
 
-def call(fn: str, *args) -> None:
+def call(fn: str, *args, opts: LpOpts | None = None) -> None:
+    """Call ``fn``; entries whose last parameter is ``const lp_opts_t*`` get ``opts`` (NULL by default)."""
+    if SIGNATURES[fn][1] and SIGNATURES[fn][1][-1] is _OPTS_PTR:
+        args = args + (ctypes.byref(opts) if opts is not None else None,)
     check(fn, getattr(load(), fn)(*args))
 
 

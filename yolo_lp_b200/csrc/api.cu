@@ -1,7 +1,7 @@
 // extern "C" boundary of liblpnms.so (see include/lpnms.h): argument validation, workspace
 // carving and kernel launches.  No allocation, no synchronisation; the only process-global state
-// is idempotent per-device caches (SM count, kernel attributes) and the two documented
-// debug / tuning hooks (lp_debug_nms_timing, lp_tune).
+// is idempotent per-device caches (SM count, kernel attributes, the tensor-map encoder).  Tuning and
+// debug knobs travel with the call (lp_opts_t), so concurrent callers never see each other's.
 #include <math.h>
 #include <stdio.h>
 
@@ -91,34 +91,25 @@ LP_API int lp_nms_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) 
     return LP_OK;
 }
 
-// Debug hook (not part of the product ABI, not thread-safe): when set, K2 writes clock64 stamps
-// of its phases for every image into buf[B][8].  Used by tools/nms_phase_timing.py only.
-static long long* g_debug_timing = nullptr;
-LP_API int lp_debug_nms_timing(long long* buf) {
-    g_debug_timing = buf;
-    return LP_OK;
-}
-
-// Tuning hook (process-global, not thread-safe; defaults are right for production): key 0 = upper
-// bound on the CTAs of K1 (0 = one per SM).  Leaving some SMs to K2 lets the NMS of batch i overlap
-// the filter of batch i+1 when the two stages are driven from two streams.
-static int g_filter_cta_limit = 0;
-static int g_decode_tma = 1;   // key 1: 0 = force the cp.async load path of the decode kernel
-LP_API int lp_tune(int key, int value) {
-    if (key == 0 && value >= 0) {
-        g_filter_cta_limit = value;
-        return LP_OK;
+// Per-call knobs (lp_opts_t, NULL = production defaults), resolved once per entry.
+struct Opts {
+    int ctas = 0;                 // CTA count of K1 / KF; 0 = the heuristics below
+    bool tma = true;              // TMA variants of the decode / fused kernels when the shapes allow
+    long long* timing = nullptr;  // debug: device buffer for clock64 stamps
+};
+static Opts resolve(const lp_opts_t* o) {
+    Opts r;
+    if (o) {
+        r.ctas = o->filter_ctas > 0 ? o->filter_ctas : 0;
+        r.tma = o->no_tma == 0;
+        r.timing = o->timing;
     }
-    if (key == 1) {
-        g_decode_tma = value != 0;
-        return LP_OK;
-    }
-    return LP_E_ARG;
+    return r;
 }
 
 // shared validation + parameter setup of the two NMS stages
 static int nms_setup(const float* pred, int B, int A, int max_det, void* workspace, size_t workspace_bytes,
-                     FilterParams& f, NmsParams& n, bool need_pred = true) {
+                     FilterParams& f, NmsParams& n, const Opts& o, bool need_pred = true) {
     if ((need_pred && !pred) || !workspace) return LP_E_NULL;
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
     if ((need_pred && !aligned(pred, 16)) || !aligned(workspace, WS_ALIGN)) return LP_E_ALIGN;
@@ -150,7 +141,7 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     n.rescale = nullptr;
     n.do_round = 0;
     n.sort_smem_keys = nms_sort_smem_keys((unsigned)A);
-    n.timing = g_debug_timing;
+    n.timing = o.timing;
     n.from_levels = 0;
     n.half_input = 0;
     n.rearm = 0;
@@ -159,14 +150,40 @@ static int nms_setup(const float* pred, int B, int A, int max_det, void* workspa
     return LP_OK;
 }
 
+// Everything lp_nms_* can reject, checked before anything is queued (a step that failed half way
+// would leave the workspace's candidate counters non-zero behind a caller who believes it re-armed).
+static int nms_validate(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                        const void* workspace, size_t workspace_bytes, const float* out, const int* counts) {
+    if (!pred || !workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (!size_ok(B, A, max_det) || max_nms <= 0) return LP_E_SIZE;
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
+    return LP_OK;
+}
+
+// K1's grid: it saturates HBM with roughly half the SMs (one 217 KB CTA each); the rest is left free
+// so that K2 of the previous batch (one CTA per image, driven from a second stream) can run
+// concurrently instead of queueing behind K1's persistent CTAs.  Another ninth of the SMs (16 of 148)
+// is left free beyond that: with the filter alternating between two streams the next batch's first
+// CTAs start there at once, and K1 alone is no slower (measured at cfg2 / cfg5: 100 CTAs 43.2 /
+// 169.9 us per pipelined step, 116 CTAs 44.4 / 171.9).
+static int filter_ctas(int B, const Opts& o) {
+    const int sms = num_sms_cached();
+    if (o.ctas > 0) return o.ctas < sms ? o.ctas : sms;
+    int ctas = sms - (B < sms / 2 ? B : sms / 2) - sms / 9;
+    if (ctas < sms - sms * 7 / 16) ctas = sms - sms * 7 / 16;   // 84 of 148 still saturate HBM
+    return ctas;
+}
+
 // armed: the last kernel that ran on this workspace was a K2 launched with rearm (it zeroed the
 // candidate counts and the tile counter), so the memset node in front of the filter kernel is skipped
 static int nms_filter(const float* pred, int B, int A, double conf_thres, void* workspace, size_t workspace_bytes,
-                      lp_stream_t stream, bool armed, bool half = false) {
+                      lp_stream_t stream, const Opts& o, bool armed, bool half) {
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     FilterParams f;
     NmsParams n;
-    const int rc = nms_setup(pred, B, A, 0, workspace, (size_t)-1, f, n);
+    const int rc = nms_setup(pred, B, A, 0, workspace, (size_t)-1, f, n, o);
     if (rc != LP_OK) return rc;
     // the layout up to the keys does not depend on max_det; require at least counts + keys
     const WsLayout w = ws_layout(B, A, 0);
@@ -177,34 +194,20 @@ static int nms_filter(const float* pred, int B, int A, double conf_thres, void* 
         if (e != cudaSuccess) return (int)e;
     }
     f.conf = (float)conf_thres;  // tensor >= python-scalar compares in fp32
-    // K1 saturates HBM with roughly half the SMs (one 217 KB CTA each); the rest is left free so
-    // that K2 of the previous batch (one CTA per image, driven from a second stream) can run
-    // concurrently instead of queueing behind K1's persistent CTAs.
-    // Another ninth of the SMs (16 of 148) is left free beyond that: with the filter alternating
-    // between two streams the next batch's first CTAs start there at once, and K1 alone is no slower
-    // (measured at cfg2 / cfg5: 100 CTAs 43.2 / 169.9 us per pipelined step, 116 CTAs 44.4 / 171.9).
-    const int sms = num_sms_cached();
-    int ctas = sms - (B < sms / 2 ? B : sms / 2) - sms / 9;
-    if (ctas < sms - sms * 7 / 16) ctas = sms - sms * 7 / 16;   // 84 of 148 still saturate HBM
-    if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < sms ? g_filter_cta_limit : sms;
+    const int ctas = filter_ctas(B, o);
     return (int)(half ? launch_filter_half(f, ctas, s) : launch_filter(f, ctas, s));
-}
-
-LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
-                             size_t workspace_bytes, lp_stream_t stream) {
-    return nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, stream, false);
 }
 
 static int nms_suppress(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms, void* workspace,
                         size_t workspace_bytes, float* out, int* counts, int* kept_anchor, const float* rescale,
-                        int do_round, lp_stream_t stream, bool rearm, bool half = false) {
+                        int do_round, lp_stream_t stream, const Opts& o, bool rearm, bool half) {
     if (!counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0) return LP_E_SIZE;
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
     if (!aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
     FilterParams f;
     NmsParams n;
-    const int rc = nms_setup(pred, B, A, max_det, workspace, workspace_bytes, f, n);
+    const int rc = nms_setup(pred, B, A, max_det, workspace, workspace_bytes, f, n, o);
     if (rc != LP_OK) return rc;
     // (double)ovr > iou_thres  <=>  ovr > largest float <= iou_thres
     float iou_floor = (float)iou_thres;
@@ -221,18 +224,13 @@ static int nms_suppress(const float* pred, int B, int A, double iou_thres, int m
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
-LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
-                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                               const float* rescale, int do_round, lp_stream_t stream) {
-    return nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
-                        rescale, do_round, stream, false);
-}
-
-static int nms_pipelined(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
-                         void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                         const float* rescale, int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
-                         void* workspace_free_event, void* filtered_event, void* done_event, void* time_begin_event,
-                         void* time_end_event, bool half) {
+// The event choreography of one pipelined step, shared by the NMS and the fused entries: `filter`
+// queues K1 / KF on the filter stream, `suppress` K2 on the NMS stream.
+extern "C++" {
+template <class Filter, class Suppress>
+static int pipelined_step(lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
+                          void* filtered_event, void* done_event, void* time_begin_event, void* time_end_event,
+                          Filter filter, Suppress suppress) {
     if (!filtered_event) return LP_E_NULL;
     cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
     cudaError_t e;
@@ -245,7 +243,7 @@ static int nms_pipelined(const float* pred, int B, int A, double conf_thres, dou
         if (e != cudaSuccess) return (int)e;
     }
     // a workspace that comes with the done_event of its previous step was re-armed by that step's K2
-    int rc = nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream, workspace_free_event != nullptr, half);
+    int rc = filter(workspace_free_event != nullptr);
     if (rc != LP_OK) return rc;
     if (time_end_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
@@ -255,8 +253,7 @@ static int nms_pipelined(const float* pred, int B, int A, double conf_thres, dou
     if (e != cudaSuccess) return (int)e;
     e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
     if (e != cudaSuccess) return (int)e;
-    rc = nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
-                      rescale, do_round, nms_stream, true, half);
+    rc = suppress();
     if (rc != LP_OK) return rc;
     if (done_event) {
         e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
@@ -264,50 +261,89 @@ static int nms_pipelined(const float* pred, int B, int A, double conf_thres, dou
     }
     return LP_OK;
 }
+}  // extern "C++"
 
+static int nms_pipelined(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                         void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                         const float* rescale, int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
+                         void* workspace_free_event, void* filtered_event, void* done_event, void* time_begin_event,
+                         void* time_end_event, const lp_opts_t* opts, bool half) {
+    const int rc = nms_validate(pred, B, A, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts);
+    if (rc != LP_OK) return rc;
+    const Opts o = resolve(opts);
+    return pipelined_step(
+        filter_stream, nms_stream, workspace_free_event, filtered_event, done_event, time_begin_event, time_end_event,
+        [&](bool armed) { return nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, filter_stream, o, armed, half); },
+        [&]() {
+            return nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                                rescale, do_round, nms_stream, o, true, half);
+        });
+}
+
+static int nms_serial(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                      const float* rescale, int do_round, lp_stream_t stream, const lp_opts_t* opts, bool half) {
+    int rc = nms_validate(pred, B, A, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts);
+    if (rc != LP_OK) return rc;
+    const Opts o = resolve(opts);
+    rc = nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, stream, o, false, half);
+    if (rc != LP_OK) return rc;
+    return nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor, rescale,
+                        do_round, stream, o, false, half);
+}
+
+LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                      const float* rescale, int do_round, lp_stream_t stream, const lp_opts_t* opts) {
+    return nms_serial(pred, B, A, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                      kept_anchor, rescale, do_round, stream, opts, false);
+}
+LP_API int lp_nms_filter_f32(const float* pred, int B, int A, double conf_thres, void* workspace,
+                             size_t workspace_bytes, lp_stream_t stream, const lp_opts_t* opts) {
+    return nms_filter(pred, B, A, conf_thres, workspace, workspace_bytes, stream, resolve(opts), false, false);
+}
+LP_API int lp_nms_suppress_f32(const float* pred, int B, int A, double iou_thres, int max_det, int max_nms,
+                               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                               const float* rescale, int do_round, lp_stream_t stream, const lp_opts_t* opts) {
+    return nms_suppress(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
+                        rescale, do_round, stream, resolve(opts), false, false);
+}
 LP_API int lp_nms_pipelined_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
                                 int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                 int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
                                 lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                void* done_event, void* time_begin_event, void* time_end_event) {
+                                void* done_event, void* time_begin_event, void* time_end_event, const lp_opts_t* opts) {
     return nms_pipelined(pred, B, A, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
                          kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event, filtered_event,
-                         done_event, time_begin_event, time_end_event, false);
+                         done_event, time_begin_event, time_end_event, opts, false);
 }
 
 // ---- fp16 head tensors: pred holds IEEE halves, results == the f32 entries on pred.float()
+LP_API int lp_nms_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
+                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
+                      const float* rescale, int do_round, lp_stream_t stream, const lp_opts_t* opts) {
+    return nms_serial(static_cast<const float*>(pred), B, A, conf_thres, iou_thres, max_det, max_nms, workspace,
+                      workspace_bytes, out, counts, kept_anchor, rescale, do_round, stream, opts, true);
+}
 LP_API int lp_nms_filter_f16(const void* pred, int B, int A, double conf_thres, void* workspace, size_t workspace_bytes,
-                             lp_stream_t stream) {
-    return nms_filter(static_cast<const float*>(pred), B, A, conf_thres, workspace, workspace_bytes, stream, false, true);
+                             lp_stream_t stream, const lp_opts_t* opts) {
+    return nms_filter(static_cast<const float*>(pred), B, A, conf_thres, workspace, workspace_bytes, stream, resolve(opts),
+                      false, true);
 }
 LP_API int lp_nms_suppress_f16(const void* pred, int B, int A, double iou_thres, int max_det, int max_nms, void* workspace,
                                size_t workspace_bytes, float* out, int* counts, int* kept_anchor, const float* rescale,
-                               int do_round, lp_stream_t stream) {
+                               int do_round, lp_stream_t stream, const lp_opts_t* opts) {
     return nms_suppress(static_cast<const float*>(pred), B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
-                        counts, kept_anchor, rescale, do_round, stream, false, true);
-}
-LP_API int lp_nms_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
-                      void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                      const float* rescale, int do_round, lp_stream_t stream) {
-    // validate everything before queueing anything
-    if (!pred || !workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
-    if (!size_ok(B, A, max_det) || max_nms <= 0) return LP_E_SIZE;
-    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
-    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
-    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
-    int rc = lp_nms_filter_f16(pred, B, A, conf_thres, workspace, workspace_bytes, stream);
-    if (rc != LP_OK) return rc;
-    return lp_nms_suppress_f16(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts, kept_anchor,
-                               rescale, do_round, stream);
+                        counts, kept_anchor, rescale, do_round, stream, resolve(opts), false, true);
 }
 LP_API int lp_nms_pipelined_f16(const void* pred, int B, int A, double conf_thres, double iou_thres, int max_det,
                                 int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
                                 int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
                                 lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
-                                void* done_event, void* time_begin_event, void* time_end_event) {
+                                void* done_event, void* time_begin_event, void* time_end_event, const lp_opts_t* opts) {
     return nms_pipelined(static_cast<const float*>(pred), B, A, conf_thres, iou_thres, max_det, max_nms, workspace,
                          workspace_bytes, out, counts, kept_anchor, rescale, do_round, filter_stream, nms_stream,
-                         workspace_free_event, filtered_event, done_event, time_begin_event, time_end_event, true);
+                         workspace_free_event, filtered_event, done_event, time_begin_event, time_end_event, opts, true);
 }
 
 LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_bytes) {
@@ -315,21 +351,6 @@ LP_API int lp_detect_workspace_bytes(int B, int A, int max_det, size_t* out_byte
     if (!size_ok(B, A, max_det)) return LP_E_SIZE;
     *out_bytes = ws_layout(B, A, max_det).total_fused;
     return LP_OK;
-}
-
-LP_API int lp_nms_f32(const float* pred, int B, int A, double conf_thres, double iou_thres, int max_det, int max_nms,
-               void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-               const float* rescale, int do_round, lp_stream_t stream) {
-    // validate everything before queueing anything
-    if (!pred || !workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
-    if (!size_ok(B, A, max_det) || max_nms <= 0) return LP_E_SIZE;
-    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
-    if (!aligned(pred, 16) || !aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
-    if (workspace_bytes < ws_layout(B, A, max_det).total) return LP_E_WORKSPACE;
-    int rc = lp_nms_filter_f32(pred, B, A, conf_thres, workspace, workspace_bytes, stream);
-    if (rc != LP_OK) return rc;
-    return lp_nms_suppress_f32(pred, B, A, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
-                               kept_anchor, rescale, do_round, stream);
 }
 
 // cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
@@ -414,9 +435,11 @@ static int build_levels(const lp_level_t* levels, int n_levels, int B, DecodeLev
     return LP_OK;
 }
 
-LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream) {
+LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream,
+                                const lp_opts_t* opts) {
     if (!out) return LP_E_NULL;
     if (!aligned(out, 8)) return LP_E_ALIGN;
+    const Opts o = resolve(opts);
     DecodeParams p;
     int A = 0, tiles = 0;
     bool bulk = false;
@@ -428,17 +451,40 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     p.n_tiles = tiles * B;
     p.bulk_in = bulk ? 1 : 0;
     p.out = out;
-    p.timing = g_debug_timing;
+    p.timing = o.timing;
     DecodeMaps maps;
-    if (bulk && g_decode_tma && aligned(out, 16) && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
+    if (bulk && o.tma && aligned(out, 16) && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
     return (int)launch_decode(p, p.bulk_in == 2 ? &maps : nullptr, num_sms_cached(), static_cast<cudaStream_t>(stream));
+}
+
+// Everything the fused entries can reject (apart from the fp16 shape rule, which needs the tensor
+// maps), checked before anything is queued.
+static int detect_validate(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres, int max_det,
+                           int max_nms, const void* workspace, size_t workspace_bytes, const float* out, const int* counts,
+                           bool half) {
+    if (!workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
+    if (max_nms <= 0 || max_det < 0) return LP_E_SIZE;
+    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
+    DecodeLevel lv[LP_MAX_LEVELS];
+    int A = 0, tiles = 0;
+    bool bulk = false;
+    const int rc = build_levels(levels, n_levels, B, lv, A, tiles, bulk);
+    if (rc != LP_OK) return rc;
+    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
+    if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
+    if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
+    if (half) {
+        if (!bulk) return LP_E_ARG;
+        for (int l = 0; l < n_levels; ++l)
+            if (lv[l].hw % 8 != 0) return LP_E_ARG;
+    }
+    return LP_OK;
 }
 
 // overlapped: the caller runs K2 of another batch concurrently (the pipelined entry and the stand-alone
 // stage entry, which exists for exactly that); false for the serial one-call path
 static int detect_filter(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det, void* workspace,
-                         size_t workspace_bytes, lp_stream_t stream, bool overlapped, bool armed = false,
-                         bool half = false) {
+                         size_t workspace_bytes, lp_stream_t stream, const Opts& o, bool overlapped, bool armed, bool half) {
     if (max_det < 0) return LP_E_SIZE;
     if (!(conf_thres >= 0.0 && conf_thres <= 1.0)) return LP_E_THRESHOLD;
     LevelsFilterParams k;
@@ -448,16 +494,11 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
     if (rc != LP_OK) return rc;
     FilterParams f;
     NmsParams n;
-    rc = nms_setup(nullptr, B, A, 0, workspace, (size_t)-1, f, n, false);
+    rc = nms_setup(nullptr, B, A, 0, workspace, (size_t)-1, f, n, o, false);
     if (rc != LP_OK) return rc;
     // the fused layout depends on max_det through the kept_* arrays that precede slot_of / rec
     const WsLayout w = ws_layout(B, A, max_det);
     if (workspace_bytes < w.total_fused) return LP_E_WORKSPACE;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (!armed) {
-        const cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
-        if (e != cudaSuccess) return (int)e;
-    }
     k.A = A;
     k.rec = reinterpret_cast<float*>(static_cast<char*>(workspace) + w.rec);
     k.slot_of = reinterpret_cast<unsigned*>(static_cast<char*>(workspace) + w.slot_of);
@@ -469,7 +510,7 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
     k.counts = f.counts;
     k.key_stride = f.key_stride;
     k.tile_counter = f.tile_counter;
-    k.timing = g_debug_timing;
+    k.timing = o.timing;
     DecodeMaps maps;
     k.half_levels = half ? 1 : 0;
     bool tma;
@@ -481,7 +522,12 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
         if (!bulk || !build_decode_maps(k.lv, n_levels, B, maps, NGROUP, true)) return LP_E_ARG;
         tma = true;
     } else {
-        tma = bulk && g_decode_tma && build_decode_maps(k.lv, n_levels, B, maps, NGROUP);
+        tma = bulk && o.tma && build_decode_maps(k.lv, n_levels, B, maps, NGROUP);
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!armed) {   // nothing is queued before the last check above has passed
+        const cudaError_t e = cudaMemsetAsync(f.counts, 0, sizeof(int) * ((size_t)B + 1), s);
+        if (e != cudaSuccess) return (int)e;
     }
     // like K1: one persistent CTA per SM, some SMs left free for K2 of the previous batch.  The
     // register-resident kernel is latency-bound and wants more SMs than K1 (a sixth left free is the
@@ -492,18 +538,13 @@ static int detect_filter(const lp_level_t* levels, int n_levels, int B, double c
     int ctas = num_sms_cached();
     const int spare = tma && overlapped ? ctas / 2 : ctas / 6;
     ctas -= B < spare ? B : spare;
-    if (g_filter_cta_limit > 0) ctas = g_filter_cta_limit < num_sms_cached() ? g_filter_cta_limit : num_sms_cached();
+    if (o.ctas > 0) ctas = o.ctas < num_sms_cached() ? o.ctas : num_sms_cached();
     return (int)launch_levels_filter(k, tma ? &maps : nullptr, ctas, s);
-}
-
-LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
-                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
-    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, true);
 }
 
 static int detect_suppress(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det, int max_nms,
                            void* workspace, size_t workspace_bytes, float* out, int* counts, int* kept_anchor,
-                           const float* rescale, int do_round, lp_stream_t stream, bool rearm) {
+                           const float* rescale, int do_round, lp_stream_t stream, const Opts& o, bool rearm) {
     if (!counts || (!out && max_det > 0)) return LP_E_NULL;
     if (max_nms <= 0) return LP_E_SIZE;
     if (!(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
@@ -515,7 +556,7 @@ static int detect_suppress(const lp_level_t* levels, int n_levels, int B, double
     bool bulk = false;
     int rc = build_levels(levels, n_levels, B, lv, A, tiles, bulk);
     if (rc != LP_OK) return rc;
-    rc = nms_setup(nullptr, B, A, max_det, workspace, workspace_bytes, f, n, false);
+    rc = nms_setup(nullptr, B, A, max_det, workspace, workspace_bytes, f, n, o, false);
     if (rc != LP_OK) return rc;
     if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
     float iou_floor = (float)iou_thres;
@@ -532,45 +573,64 @@ static int detect_suppress(const lp_level_t* levels, int n_levels, int B, double
     return (int)launch_nms(n, B, static_cast<cudaStream_t>(stream));
 }
 
-LP_API int lp_detect_filter_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
-                                void* workspace, size_t workspace_bytes, lp_stream_t stream) {
-    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, true, false, true);
-}
-
-LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
-                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream) {
-    return detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
-                           kept_anchor, rescale, do_round, stream, false);
-}
-
 static int detect_postprocess(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
                               int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                              int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream, bool half) {
-    // validate everything before queueing anything
-    if (!workspace || !counts || (!out && max_det > 0)) return LP_E_NULL;
-    if (max_nms <= 0 || max_det < 0) return LP_E_SIZE;
-    if (!(conf_thres >= 0.0 && conf_thres <= 1.0) || !(iou_thres >= 0.0 && iou_thres <= 1.0)) return LP_E_THRESHOLD;
-    DecodeLevel lv[LP_MAX_LEVELS];
-    int A = 0, tiles = 0;
-    bool bulk = false;
-    int rc = build_levels(levels, n_levels, B, lv, A, tiles, bulk);
+                              int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream,
+                              const lp_opts_t* opts, bool half) {
+    int rc = detect_validate(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                             counts, half);
     if (rc != LP_OK) return rc;
-    if (!size_ok(B, A, max_det)) return LP_E_SIZE;
-    if (!aligned(workspace, WS_ALIGN) || !aligned(out, 4) || !aligned(counts, 4)) return LP_E_ALIGN;
-    if (workspace_bytes < ws_layout(B, A, max_det).total_fused) return LP_E_WORKSPACE;
-    rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, false, false, half);
+    const Opts o = resolve(opts);
+    rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, o, false, false, half);
     if (rc != LP_OK) return rc;
-    return lp_detect_suppress_f32(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
-                                  kept_anchor, rescale, do_round, stream);
+    return detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                           kept_anchor, rescale, do_round, stream, o, false);
 }
 
+static int detect_pipelined(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres, int max_det,
+                            int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                            int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
+                            lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event, void* done_event,
+                            void* time_begin_event, void* time_end_event, const lp_opts_t* opts, bool half) {
+    const int rc = detect_validate(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes,
+                                   out, counts, half);
+    if (rc != LP_OK) return rc;
+    const Opts o = resolve(opts);
+    return pipelined_step(
+        filter_stream, nms_stream, workspace_free_event, filtered_event, done_event, time_begin_event, time_end_event,
+        [&](bool armed) {
+            return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream, o, true,
+                                 armed, half);
+        },
+        [&]() {
+            return detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                                   kept_anchor, rescale, do_round, nms_stream, o, true);
+        });
+}
+
+LP_API int lp_detect_filter_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream, const lp_opts_t* opts) {
+    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, resolve(opts), true,
+                         false, false);
+}
+LP_API int lp_detect_filter_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, int max_det,
+                                void* workspace, size_t workspace_bytes, lp_stream_t stream, const lp_opts_t* opts) {
+    return detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, stream, resolve(opts), true,
+                         false, true);
+}
+LP_API int lp_detect_suppress_f32(const lp_level_t* levels, int n_levels, int B, double iou_thres, int max_det,
+                                  int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                  int* kept_anchor, const float* rescale, int do_round, lp_stream_t stream,
+                                  const lp_opts_t* opts) {
+    return detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
+                           kept_anchor, rescale, do_round, stream, resolve(opts), false);
+}
 LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
                                      int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
                                      int* counts, int* kept_anchor, const float* rescale, int do_round,
-                                     lp_stream_t stream) {
+                                     lp_stream_t stream, const lp_opts_t* opts) {
     return detect_postprocess(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
-                              counts, kept_anchor, rescale, do_round, stream, false);
+                              counts, kept_anchor, rescale, do_round, stream, opts, false);
 }
 // fp16 level tensors (the pointers of lp_level_t then address IEEE halves): results == the f32 entry on
 // the upcast tensors.  LP_E_ARG when a level's h*w is not a multiple of 8 or a tensor is not 16-byte
@@ -578,67 +638,29 @@ LP_API int lp_detect_postprocess_f32(const lp_level_t* levels, int n_levels, int
 LP_API int lp_detect_postprocess_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
                                      int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
                                      int* counts, int* kept_anchor, const float* rescale, int do_round,
-                                     lp_stream_t stream) {
+                                     lp_stream_t stream, const lp_opts_t* opts) {
     return detect_postprocess(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
-                              counts, kept_anchor, rescale, do_round, stream, true);
+                              counts, kept_anchor, rescale, do_round, stream, opts, true);
 }
-
-static int detect_pipelined(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres, int max_det,
-                            int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
-                            int* kept_anchor, const float* rescale, int do_round, lp_stream_t filter_stream,
-                            lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event, void* done_event,
-                            void* time_begin_event, void* time_end_event, bool half) {
-    if (!filtered_event) return LP_E_NULL;
-    cudaStream_t sf = static_cast<cudaStream_t>(filter_stream), sn = static_cast<cudaStream_t>(nms_stream);
-    cudaError_t e;
-    if (workspace_free_event) {
-        e = cudaStreamWaitEvent(sf, static_cast<cudaEvent_t>(workspace_free_event), 0);
-        if (e != cudaSuccess) return (int)e;
-    }
-    if (time_begin_event) {
-        e = cudaEventRecord(static_cast<cudaEvent_t>(time_begin_event), sf);
-        if (e != cudaSuccess) return (int)e;
-    }
-    int rc = detect_filter(levels, n_levels, B, conf_thres, max_det, workspace, workspace_bytes, filter_stream, true,
-                           workspace_free_event != nullptr, half);
-    if (rc != LP_OK) return rc;
-    if (time_end_event) {
-        e = cudaEventRecord(static_cast<cudaEvent_t>(time_end_event), sf);
-        if (e != cudaSuccess) return (int)e;
-    }
-    e = cudaEventRecord(static_cast<cudaEvent_t>(filtered_event), sf);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaStreamWaitEvent(sn, static_cast<cudaEvent_t>(filtered_event), 0);
-    if (e != cudaSuccess) return (int)e;
-    rc = detect_suppress(levels, n_levels, B, iou_thres, max_det, max_nms, workspace, workspace_bytes, out, counts,
-                         kept_anchor, rescale, do_round, nms_stream, true);
-    if (rc != LP_OK) return rc;
-    if (done_event) {
-        e = cudaEventRecord(static_cast<cudaEvent_t>(done_event), sn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    return LP_OK;
-}
-
 LP_API int lp_detect_pipelined_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
                                    int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
                                    int* counts, int* kept_anchor, const float* rescale, int do_round,
                                    lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
                                    void* filtered_event, void* done_event, void* time_begin_event,
-                                   void* time_end_event) {
+                                   void* time_end_event, const lp_opts_t* opts) {
     return detect_pipelined(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
                             counts, kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
-                            filtered_event, done_event, time_begin_event, time_end_event, false);
+                            filtered_event, done_event, time_begin_event, time_end_event, opts, false);
 }
 LP_API int lp_detect_pipelined_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
                                    int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
                                    int* counts, int* kept_anchor, const float* rescale, int do_round,
                                    lp_stream_t filter_stream, lp_stream_t nms_stream, void* workspace_free_event,
                                    void* filtered_event, void* done_event, void* time_begin_event,
-                                   void* time_end_event) {
+                                   void* time_end_event, const lp_opts_t* opts) {
     return detect_pipelined(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
                             counts, kept_anchor, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
-                            filtered_event, done_event, time_begin_event, time_end_event, true);
+                            filtered_event, done_event, time_begin_event, time_end_event, opts, true);
 }
 
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream) {
@@ -743,7 +765,7 @@ LP_API int lp_eval_match_f32(const float* det, const int* counts, int B, int max
     if (!det || !counts || !targets || !target_image || !match) return LP_E_NULL;
     if (B <= 0 || max_det <= 0 || T < 0) return LP_E_SIZE;
     if (!aligned(det, 16)) return LP_E_ALIGN;
-    return (int)launch_eval_match(det, counts, max_det, targets, target_image, T, match, static_cast<cudaStream_t>(stream));
+    return (int)launch_eval_match(det, counts, B, max_det, targets, target_image, T, match, static_cast<cudaStream_t>(stream));
 }
 
 // Counters and summary of Evaler.eval (yolov6/core/evaler.py:160-283) from the per-target matches,

@@ -126,16 +126,17 @@ __global__ void prepare_targets_kernel(const float* __restrict__ in, int T, floa
 // maximum (torch.max, :190), then the corner test (:218) and the 8-character test (:223-226)
 // against the matched prediction.  match[t] = { t_iou, match index, is_cor, is_cls };
 // t_iou = -1 marks an image without predictions (the reference skips it, :188).
-__global__ void eval_match_kernel(const float* __restrict__ det, const int* __restrict__ counts, int max_det,
+__global__ void eval_match_kernel(const float* __restrict__ det, const int* __restrict__ counts, int B, int max_det,
                                   const float* __restrict__ targets, const int* __restrict__ target_image, int T,
                                   float* __restrict__ match) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= T) return;
     const int b = target_image[t];
-    const int n = min(counts[b], max_det);
-    const float* tg = targets + (size_t)t * 20;
-    const float* rows = det + (size_t)b * max_det * OUTW;
     float* o = match + (size_t)t * 4;
+    // a target whose image index is outside the batch reads nothing (the host accumulator rejects it)
+    const int n = (b >= 0 && b < B) ? min(counts[b], max_det) : 0;
+    const float* tg = targets + (size_t)t * 20;
+    const float* rows = det + (size_t)(n > 0 ? b : 0) * max_det * OUTW;
     if (n <= 0) {
         if (lane == 0) { o[0] = -1.0f; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; }
         return;
@@ -219,10 +220,10 @@ cudaError_t launch_prepare_targets(const float* in, int T, float w, float h, flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_eval_match(const float* det, const int* counts, int max_det, const float* targets,
+cudaError_t launch_eval_match(const float* det, const int* counts, int B, int max_det, const float* targets,
                               const int* target_image, int T, float* match, cudaStream_t s) {
     if (T <= 0) return cudaSuccess;
-    eval_match_kernel<<<blocks_for((long long)T * 32, 128), 128, 0, s>>>(det, counts, max_det, targets, target_image, T, match);
+    eval_match_kernel<<<blocks_for((long long)T * 32, 128), 128, 0, s>>>(det, counts, B, max_det, targets, target_image, T, match);
     return cudaGetLastError();
 }
 

@@ -129,7 +129,7 @@ cudaError_t launch_rescale_batch(float* det, const int* counts, int B, int max_d
                                  cudaStream_t s);
 
 cudaError_t launch_prepare_targets(const float* in, int T, float w, float h, float* out, int* out_image, cudaStream_t s);
-cudaError_t launch_eval_match(const float* det, const int* counts, int max_det, const float* targets,
+cudaError_t launch_eval_match(const float* det, const int* counts, int B, int max_det, const float* targets,
                               const int* target_image, int T, float* match, cudaStream_t s);
 cudaError_t launch_txt_records(const float* det, const int* counts, int B, int max_det, const float* src_wh, float* rec,
                                cudaStream_t s);

@@ -140,10 +140,12 @@ class DecodePlan(_LevelTable):
         elif tuple(out.shape) != (B, A, ROW) or out.dtype != torch.float32 or not out.is_contiguous():
             raise ValueError("out must be a contiguous fp32 [B, A, 290] tensor")
         self.out = out
+        self.opts = None   # _abi.opts(...): per-call knobs (tests, tools); None = production
 
     def run(self) -> torch.Tensor:
         with torch.cuda.device(self.device):
-            _abi.call("lp_detect_decode_f32", self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device))
+            _abi.call("lp_detect_decode_f32", self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device),
+                      opts=self.opts)
         return self.out
 
 
@@ -167,6 +169,7 @@ class PostprocessPlan(_LevelTable):
         # True while the last thing enqueued on this workspace was a pipelined step (whose K2 leaves the
         # candidate counters zeroed): only then may the next pipelined step skip its memset
         self.armed = False
+        self.opts = None   # _abi.opts(...): per-call knobs (tests, tools); None = production
 
     def run(self, conf_thres, iou_thres, rescale=None, do_round=False):
         self.armed = False
@@ -175,21 +178,23 @@ class PostprocessPlan(_LevelTable):
                       self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
                       self.out.data_ptr(), self.counts.data_ptr(),
                       self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
-                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device))
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device),
+                      opts=self.opts)
         return self.out, self.counts
 
     def run_filter(self, conf_thres):
         self.armed = False
         with torch.cuda.device(self.device):
             _abi.call("lp_detect_filter" + self._sfx, self.arr, self.n, self.B, float(conf_thres), self.max_det,
-                      self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device))
+                      self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device), opts=self.opts)
 
     def run_suppress(self, iou_thres, rescale=None, do_round=False):
         with torch.cuda.device(self.device):
             _abi.call("lp_detect_suppress_f32", self.arr, self.n, self.B, float(iou_thres), self.max_det, self.max_nms,
                       self.workspace.data_ptr(), self.workspace.numel(), self.out.data_ptr(), self.counts.data_ptr(),
                       self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
-                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device))
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), _stream(self.device),
+                      opts=self.opts)
         return self.out, self.counts
 
     def candidate_counts(self) -> torch.Tensor:
@@ -233,13 +238,14 @@ class PostprocessPipeline:
             for ev in timing:
                 if ev.cuda_event == 0:
                     ev.record(s_filter)
+        armed, plan.armed = plan.armed, False   # re-armed only once the whole step has been queued
         _abi.call("lp_detect_pipelined" + plan._sfx, plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, s_filter.cuda_stream, self.s_nms.cuda_stream,
-                  self.done[slot].cuda_event if plan.armed else None,
+                  self.done[slot].cuda_event if armed else None,
                   self.filtered[slot].cuda_event, self.done[slot].cuda_event,
                   timing[0].cuda_event if timing is not None else None,
-                  timing[1].cuda_event if timing is not None else None)
+                  timing[1].cuda_event if timing is not None else None, opts=plan.opts)
         plan.armed = True
         self.n += 1
         return slot, plan.out, plan.counts

@@ -60,6 +60,7 @@ class NmsPlan:
         # True while the last thing enqueued on this workspace was a pipelined step (whose K2 leaves the
         # candidate counters zeroed): only then may the next pipelined step skip its memset
         self.armed = False
+        self.opts = None   # _abi.opts(...): per-call tuning / debug knobs (tests, tools); None = production
 
     def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, rescale: torch.Tensor | None = None,
             do_round: bool = False, out=None, counts=None):
@@ -77,7 +78,7 @@ class NmsPlan:
                       self.max_det, self.max_nms, self.workspace.data_ptr(), self.workspace.numel(),
                       out.data_ptr(), counts.data_ptr(),
                       self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
-                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), stream)
+                      rescale.data_ptr() if rescale is not None else None, int(bool(do_round)), stream, opts=self.opts)
         return out, counts
 
     def run_filter(self, pred: torch.Tensor, conf_thres: float):
@@ -86,7 +87,7 @@ class NmsPlan:
         with torch.cuda.device(self.device):
             _abi.call(_entry("lp_nms_filter", pred), pred.data_ptr(), self.B, self.A, float(conf_thres),
                       self.workspace.data_ptr(), self.workspace.numel(),
-                      torch.cuda.current_stream(self.device).cuda_stream)
+                      torch.cuda.current_stream(self.device).cuda_stream, opts=self.opts)
 
     def run_suppress(self, pred: torch.Tensor, iou_thres: float, rescale=None, do_round=False, out=None, counts=None):
         """Stage K2 only (lp_nms_suppress_f32) on what :meth:`run_filter` left behind."""
@@ -97,7 +98,7 @@ class NmsPlan:
                       self.max_nms, self.workspace.data_ptr(), self.workspace.numel(), out.data_ptr(),
                       counts.data_ptr(), self.kept_anchor.data_ptr() if self.kept_anchor is not None else None,
                       rescale.data_ptr() if rescale is not None else None, int(bool(do_round)),
-                      torch.cuda.current_stream(self.device).cuda_stream)
+                      torch.cuda.current_stream(self.device).cuda_stream, opts=self.opts)
         return out, counts
 
     def candidate_counts(self) -> torch.Tensor:
@@ -157,13 +158,16 @@ class NmsPipeline:
             for ev in timing:  # torch creates the cudaEvent_t lazily, on the first record
                 if ev.cuda_event == 0:
                     ev.record(s_filter)
+        # the workspace counts as re-armed only once the step has been queued in full: a call that
+        # raises leaves plan.armed False, so the next step on this workspace memsets its counters again
+        armed, plan.armed = plan.armed, False
         _abi.call(_entry("lp_nms_pipelined", pred), pred.data_ptr(), plan.B, plan.A, float(conf_thres), float(iou_thres),
                   plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
                   plan.counts.data_ptr(), None, None, 0, s_filter.cuda_stream, self.s_nms.cuda_stream,
-                  self.done[slot].cuda_event if plan.armed else None,
+                  self.done[slot].cuda_event if armed else None,
                   self.filtered[slot].cuda_event, self.done[slot].cuda_event,
                   timing[0].cuda_event if timing is not None else None,
-                  timing[1].cuda_event if timing is not None else None)
+                  timing[1].cuda_event if timing is not None else None, opts=plan.opts)
         plan.armed = True
         self.n += 1
         return slot, plan.out, plan.counts
