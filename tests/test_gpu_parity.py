@@ -619,10 +619,16 @@ def test_half_head_tensor_equals_fp32_path_on_the_upcast_tensor(B, A, n_pos, con
     torch.cuda.synchronize()
     for b, k in enumerate(counts.cpu().tolist()):
         assert_rows_equal(out[b, :k].cpu().numpy(), want[b], f"half pipelined[{b}]")
-    # host-buffer path: the halves travel as halves
+    # the reference-signature entry returns rows in the prediction's dtype (the reference's torch.cat,
+    # nms.py:94-96): the fp32 rows rounded once to half -- device tensor and host-buffer path (the
+    # halves travel as halves)
     host = lp.non_max_suppression(ph, conf, iou, max_det=max_det)
+    devr = lp.non_max_suppression(dev_h, conf, iou, max_det=max_det)
     for b in range(B):
-        assert_rows_equal(host[b].numpy(), want[b], f"half host path[{b}]")
+        w16 = torch.from_numpy(want[b]).half()
+        assert host[b].dtype == torch.float16 and devr[b].dtype == torch.float16 and devr[b].is_cuda
+        assert torch.equal(host[b].view(torch.int16), w16.view(torch.int16)), f"half host path[{b}]"
+        assert torch.equal(devr[b].cpu().view(torch.int16), w16.view(torch.int16)), f"half device path[{b}]"
 
 
 @pytest.mark.parametrize("B,H,W,conf", [(32, 640, 640, 0.25), (9, 640, 640, 0.001), (4, 1280, 1280, 0.25),

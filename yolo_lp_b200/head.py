@@ -283,7 +283,8 @@ _PRED_ATTRS = tuple(n + "_preds" for n in CLS_NAMES)
 def detect_forward_eval(detect, x):
     """Eval branch of the reference ``Detect.forward`` (effidehead.py:214-301) for a module
     with the reference's attribute names: the stem / cls / reg / prediction convs run as they
-    are (torch + cuDNN), everything after them is one fused kernel."""
+    are (torch + cuDNN), everything after them is one fused kernel.  (The reference also overwrites
+    the caller's list ``x[i]`` with the stem outputs, effidehead.py:237; that side effect is not kept.)"""
     if getattr(detect, "use_dfl", False):
         raise NotImplementedError("use_dfl=True (distillation heads) is outside the LP configs")
     levels = []
@@ -295,7 +296,11 @@ def detect_forward_eval(detect, x):
         lv["reg"] = detect.reg_preds[i](reg_feat)
         lv["cor"] = detect.cor_preds[i](reg_feat)
         levels.append(lv)
-    return detect_decode(levels, [float(s) for s in detect.stride])
+    out = detect_decode(levels, [float(s) for s in detect.stride])
+    # model.half() (inferer.py:46-50): the reference's head tensor is fp16, and a drop-in keeps the dtype
+    # flow -- the decode itself upcasts the conv outputs exactly and computes in fp32 (one rounding at the
+    # end instead of the reference's per-operation half arithmetic)
+    return out.half() if x[0].dtype == torch.float16 else out
 
 
 def detect_forward_nms(detect, x, conf_thres=0.25, iou_thres=0.45, max_det=300):

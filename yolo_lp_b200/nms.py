@@ -11,7 +11,15 @@ Deliberate differences from the reference:
   * ``prediction`` is NOT mutated (reference: ``x[:,13:] *= x[:,4:5]``, nms.py:76);
   * no 10 s wall-clock ``time_limit`` early exit (nms.py:63,126-128);
   * with more than 30 000 candidates the cut is (score desc, anchor asc) where the
-    reference's unstable argsort is implementation-defined (nms.py:115-116).
+    reference's unstable argsort is implementation-defined (nms.py:115-116);
+  * fp16 predictions (the reference's ``--half`` mode, inferer.py:46-50): the rows come
+    back as fp16 like the reference's (its ``torch.cat`` keeps the prediction dtype,
+    nms.py:94-96), but they are the fp32 path's rows on ``prediction.float()`` rounded
+    once to half -- every load is an exact upcast and all arithmetic is fp32 -- not the
+    reference's per-operation half arithmetic, which exists on CUDA only and sits behind
+    an unstable sort of massively tied half scores (no CPU oracle can pin it);
+  * a CPU ``prediction`` is not a fallback: it is streamed through the GPU kernels and
+    the rows come back as CPU tensors.
 """
 from __future__ import annotations
 
@@ -224,12 +232,15 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     if prediction.device.type == "cpu":
         from .host import host_pipeline
         dtype = torch.float16 if prediction.dtype == torch.float16 else torch.float32
-        return host_pipeline(B, A, max_det, dtype).run(prediction, conf_thres, iou_thres)
+        rows = host_pipeline(B, A, max_det, dtype).run(prediction, conf_thres, iou_thres)
+        return [r.half() for r in rows] if dtype == torch.float16 else rows
     pred = _device_input(prediction)
     plan = _plan_for(B, A, int(max_det), pred.device)
     out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
     _, counts = plan.run(pred, conf_thres, iou_thres, out=out)
     ks = counts.cpu().tolist()  # the one host sync of the call
+    if pred.dtype == torch.float16:   # rows in the prediction's dtype, like the reference's torch.cat
+        out = out.half()
     return [out[b, :k] for b, k in enumerate(ks)]
 
 
