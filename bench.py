@@ -11,13 +11,20 @@ N>1 is weak scaling, every rank owning its own 32-image shard of a 32*N-image ba
 collective on the data path (N=8 is configs[2]'s 256-image batch).
 
 One JSON line is printed by rank 0 with
-  value          images/s over all ranks, device-timed (CUDA events), max over ranks
+  value          images/s over all ranks: the K timed steps are ONE CUDA-graph launch of the
+                 multi-stream pipeline (K1 of step k+1 overlaps K2 of step k), CUDA events, max over ranks
   e2e            the same metric through the public API ``non_max_suppression`` with HOST
                  buffers: H2D of the head tensor from pinned memory and D2H of the detections
-                 are inside the timed region
-  roofline       K1's algorithmic bytes / its CUDA-event time vs the measured HBM peak
-  cpu_baseline   the torch-CPU port of the reference (oracle/torch_port.py) on this host
-``--impl reference`` times only that CPU port (the reference itself is not on the GPU box).
+                 are inside the timed region; ``frac_of_h2d_ceiling`` holds it against the bare
+                 concurrent pinned cudaMemcpyAsync rate of the same ranks
+  e2e_device_inputs  the production flow when the head runs on the same GPU: fused path from
+                 device-resident level tensors to HOST detections (D2H inside the timed region)
+  roofline       K1's algorithmic bytes / its CUDA-event time (8 fenced launches) vs the measured HBM peak
+  latency        p50 / p95 of one serial batch: config 1 (batch 1) and this workload
+  extras         cfg3 strong scaling (256/N images per rank), cfg5 (1280x1280) and, at N=1, cfg4,
+                 the decode kernel, the fused path and fp16 head tensors
+  cpu_baseline   the UNMODIFIED reference (oracle/_ref, staged by oracle/stage_ref.py) on this host's cores
+``--impl reference`` times only that CPU reference.
 """
 from __future__ import annotations
 
@@ -38,6 +45,9 @@ METRIC = "post-proc images/sec"
 UNIT = "images/s"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 CPU_CHUNK = 8                      # reference is driven in <= 8-image chunks (its 10 s time_limit)
+NAMES = {1: "cfg1 YOLO-LP-s 640x640 batch 1", 2: "cfg2 YOLO-LP-s 640x640 batch 32",
+         3: "cfg3 YOLO-LP-n 640x640 batch 256", 4: "cfg4 eval stress 640x640 batch 64 conf 0.001",
+         5: "cfg5 dense-plate 1280x1280 batch 32"}
 
 
 def parse():
@@ -49,37 +59,44 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="host-buffer steps (default: min(steps, 20))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the decode-kernel and fused-path side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other configs, decode, fused path, fp16)")
     return ap.parse_args()
 
 
 def workload(cid: int):
     from yolo_lp_b200 import synth
-    cfg = dict(synth.CONFIGS[cid])
-    name = {1: "cfg1 YOLO-LP-s 640x640 batch 1", 2: "cfg2 YOLO-LP-s 640x640 batch 32",
-            3: "cfg3 YOLO-LP-n 640x640 batch 256", 4: "cfg4 eval stress 640x640 batch 64 conf 0.001",
-            5: "cfg5 dense-plate 1280x1280 batch 32"}[cid]
-    return cfg, name
+    return dict(synth.CONFIGS[cid]), NAMES[cid]
 
 
 def config_block(cfg, name, n_gpus, B_local):
     return {"workload": name, "images_per_gpu": B_local, "global_batch": B_local * n_gpus, "anchors": cfg["A"],
             "row_floats": 290, "conf_thres": cfg["conf"], "iou_thres": cfg["iou"], "max_det": cfg["max_det"],
             "sharding": f"images x{n_gpus}, no collective",
-            "l2": "input %.1f MB per GPU > 126 MB L2 (no flush needed)" % (B_local * cfg["A"] * 1160 / 1e6)}
+            "l2": "input %.1f MB per GPU > 126 MB L2 (no flush needed)" % (B_local * cfg["A"] * 1160 / 1e6)
+                  if B_local * cfg["A"] * 1160 > 126e6 else
+                  "input %.1f MB per GPU fits L2: a 160 MB buffer is rewritten between timed launches" % (B_local * cfg["A"] * 1160 / 1e6)}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_pass(pred, cfg):
-    """One pass of the reference's CPU path over the sample, <= CPU_CHUNK images per call;
-    the input is cloned outside the timed region because the port mutates it like nms.py:76."""
-    import torch
+def reference_callable():
+    """The reference's own ``non_max_suppression``: the unmodified copy staged under oracle/_ref
+    (kind "reference"), else the torch-CPU port that the CPU suite pins to it (kind "port")."""
+    from oracle import stage_ref
+    if stage_ref.is_staged():
+        return stage_ref.reference().non_max_suppression, "reference", \
+            "unmodified yolov6.utils.nms.non_max_suppression (oracle/_ref) + torchvision.ops.nms"
     from oracle import torch_port
+    return torch_port.non_max_suppression, "port", "torch CPU port of nms.py + torchvision.ops.nms"
+
+
+def cpu_pass(fn, pred, cfg):
+    """One pass of the reference's CPU path over the sample, <= CPU_CHUNK images per call;
+    the input is cloned outside the timed region because the reference mutates it (nms.py:76)."""
     chunks = [pred[s:s + CPU_CHUNK].clone() for s in range(0, pred.shape[0], CPU_CHUNK)]
     t0 = time.perf_counter()
     n = 0
     for c in chunks:
-        out = torch_port.non_max_suppression(c, cfg["conf"], cfg["iou"], max_det=cfg["max_det"])
+        out = fn(c, cfg["conf"], cfg["iou"], max_det=cfg["max_det"])
         n += len(out)
     return time.perf_counter() - t0, n
 
@@ -113,21 +130,23 @@ def run_reference_arm(args):
         return
     use_all_host_threads()
     cfg, name = workload(args.config)
+    fn, kind, what = reference_callable()
     pred = cpu_sample(cfg, cpu_sample_size(args.config))
     for _ in range(max(1, args.warmup)):
-        cpu_pass(pred, cfg)
+        cpu_pass(fn, pred, cfg)
     times = []
     for _ in range(args.steps):
-        dt, _n = cpu_pass(pred, cfg)
+        dt, _n = cpu_pass(fn, pred, cfg)
         times.append(dt)
     ms = 1e3 * sum(times) / len(times)
     value = pred.shape[0] / (ms / 1e3)
-    sample = f"{pred.shape[0]} images of {name} per step, {CPU_CHUNK}-image calls, torch CPU port of nms.py + torchvision.ops.nms"
+    sample = f"{pred.shape[0]} images of {name} per step, {CPU_CHUNK}-image calls, {what}"
+    B_local = cfg["B"] if args.config != 3 else 32
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_block(cfg, name, args.gpus, cfg["B"]),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample,
+            "config": config_block(cfg, name, args.gpus, B_local),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample,
                              "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -140,8 +159,9 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.001):
         self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self.period = period
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -168,7 +188,7 @@ class ClockSampler:
     def _loop(self):
         while not self._stop.is_set():
             self._once()
-            time.sleep(0.004)
+            time.sleep(self.period)
 
     def __enter__(self):
         if self.ok:
@@ -236,7 +256,264 @@ def visible_to_physical(local_index):
     return local_index
 
 
+# --------------------------------------------------------------------------------------------- helpers
+class Ranks:
+    """Barrier / max-over-ranks plumbing (NCCL only for these two control-plane collectives)."""
+
+    def __init__(self, world, dev):
+        self.world, self.dev = world, dev
+
+    def barrier(self):
+        import torch
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def max(self, x):
+        import torch
+        if self.world == 1:
+            return x
+        import torch.distributed as dist
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+class L2Flush:
+    """Workloads smaller than the 126 MB L2 (config 1: 9.7 MB) would be timed out of cache: rewrite a
+    160 MB buffer between timed launches."""
+
+    def __init__(self, dev, needed):
+        import torch
+        self.buf = torch.empty(160 << 20, dtype=torch.uint8, device=dev) if needed else None
+
+    def __call__(self):
+        if self.buf is not None:
+            self.buf.add_(1)
+
+
+def graph_leg(ranks, pipe_factory, capture, K, W, B, clocks=None):
+    """``K`` pipelined steps as ONE graph launch, timed with CUDA events round it, max over ranks.
+    ``capture(pipe, steps)`` returns a GraphedSteps.  Warm-up: >= W steps through the same graph."""
+    import torch
+    graphed = capture(pipe_factory(), K)
+    replays = max(1, -(-W // K))
+    for _ in range(replays):
+        graphed.launch()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ranks.barrier()
+    ctx = clocks if clocks is not None else _Null()
+    with ctx:
+        h0 = time.perf_counter()
+        t0.record()
+        graphed.launch()
+        t1.record()
+        host_us = (time.perf_counter() - h0) * 1e6
+        ranks.barrier()
+    total_ms = ranks.max(t0.elapsed_time(t1))
+    return {"ms_per_step": total_ms / K, "total_ms": total_ms, "host_submit_us_per_step": host_us / K,
+            "warmup_steps_run": replays * K, "graphed": graphed}
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def eager_leg(ranks, pipe, submit, K):
+    """The same pipeline driven step by step from Python (one C call per step): what a caller
+    without a graph gets, and how much of a step the host needs to submit it."""
+    import torch
+    pipe.start()
+    for _ in range(10):
+        submit(pipe)
+    pipe.finish()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ranks.barrier()
+    t0.record()
+    h0 = time.perf_counter()
+    pipe.start()
+    for _ in range(K):
+        submit(pipe)
+    pipe.finish()
+    host_us = (time.perf_counter() - h0) * 1e6
+    t1.record()
+    ranks.barrier()
+    return ranks.max(t0.elapsed_time(t1)) / K, host_us / K
+
+
+def fenced_k1(pipe, pred, conf, iou, n=8):
+    """``n`` K1 launches inside a running pipeline, each bracketed by CUDA events on its stream and
+    fenced off from its neighbours (consecutive K1s otherwise overlap each other's drain and
+    ramp-up, and a bracket would measure queueing); K2 of the previous step runs beside them."""
+    import torch
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n)]
+    pipe.start()
+    for _ in range(4):
+        pipe.submit(pred, conf, iou)
+    for k in range(n):
+        pipe.submit(pred, conf, iou, timing=ev[k])
+        pipe.submit(pred, conf, iou)
+    pipe.finish()
+    torch.cuda.synchronize(pipe.device)
+    return [e[0].elapsed_time(e[1]) for e in ev]
+
+
+def serial_latency(plan, pred, conf, iou, n, flush):
+    """p50 / p95 of one batch run strictly serially (K1 then K2 on one stream), per-stage averages."""
+    import torch
+    for _ in range(5):
+        plan.run(pred, conf, iou)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n)]
+    torch.cuda.synchronize(plan.device)
+    for k in range(n):
+        flush()
+        ev[k][0].record()
+        plan.run_filter(pred, conf)
+        ev[k][1].record()
+        plan.run_suppress(pred, iou)
+        ev[k][2].record()
+    torch.cuda.synchronize(plan.device)
+    step = sorted(e[0].elapsed_time(e[2]) for e in ev)
+    return {"p50_ms": statistics.median(step), "p95_ms": step[int(0.95 * (n - 1))],
+            "filter_avg_ms": sum(e[0].elapsed_time(e[1]) for e in ev) / n,
+            "nms_avg_ms": sum(e[1].elapsed_time(e[2]) for e in ev) / n, "batches": n}
+
+
+def fused_latency(levels, cfg, n, flush):
+    import torch
+    from yolo_lp_b200.head import PostprocessPlan
+    plan = PostprocessPlan(levels, (8, 16, 32), cfg["max_det"])
+    for _ in range(5):
+        plan.run(cfg["conf"], cfg["iou"])
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(n)]
+    torch.cuda.synchronize(plan.device)
+    for k in range(n):
+        flush()
+        ev[k][0].record()
+        plan.run(cfg["conf"], cfg["iou"])
+        ev[k][1].record()
+    torch.cuda.synchronize(plan.device)
+    step = sorted(e[0].elapsed_time(e[1]) for e in ev)
+    return {"p50_ms": statistics.median(step), "p95_ms": step[int(0.95 * (n - 1))], "batches": n}
+
+
+def latency_block(cfg, B, pred, dev, plan, in_l2):
+    """BASELINE.json's "p50 batch latency": config 1 (tools/infer.py's batch of one image, max_det 1000)
+    and this workload, head-tensor entry (lp_nms_f32) and fused entry (lp_detect_postprocess_f32)."""
+    from yolo_lp_b200 import synth
+    from yolo_lp_b200.nms import NmsPlan
+    c1 = dict(synth.CONFIGS[1])
+    p1 = synth.synth_head(1, c1["A"], c1["img"], c1["n_plates"], c1["n_pos"], c1["seed"]).to(dev)
+    flush = L2Flush(dev, True)
+    out = {"cfg1_batch1": {"lp_nms_f32": serial_latency(NmsPlan(1, c1["A"], c1["max_det"], dev), p1, c1["conf"], c1["iou"], 100, flush),
+                           "lp_detect_postprocess_f32": fused_latency(synth.synth_levels(1, 640, 640, dev, seed=0), c1, 100, flush),
+                           "l2": "160 MB rewritten before every timed batch (the 9.7 MB input would otherwise sit in L2)"}}
+    main = serial_latency(plan, pred, cfg["conf"], cfg["iou"], 100, L2Flush(dev, in_l2))
+    out["workload"] = {"lp_nms_f32": main,
+                       "lp_detect_postprocess_f32": fused_latency(synth.synth_levels(B, cfg["img"], cfg["img"], dev, seed=cfg["seed"]),
+                                                                  cfg, 50, L2Flush(dev, in_l2))}
+    return out, main
+
+
+def h2d_ceiling(ranks, host_pred, dev_buf, reps):
+    """Bare pinned cudaMemcpyAsync rate of this rank's batch while every other rank does the same."""
+    import torch
+    s = torch.cuda.Stream(dev_buf.device)
+    with torch.cuda.stream(s):
+        dev_buf.copy_(host_pred, non_blocking=True)
+    s.synchronize()
+    ranks.barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(s):
+        for _ in range(reps):
+            dev_buf.copy_(host_pred, non_blocking=True)
+    s.synchronize()
+    ms = ranks.max((time.perf_counter() - t0) * 1e3) / reps
+    return host_pred.numel() * host_pred.element_size() / ms / 1e6   # GB/s per rank (slowest rank)
+
+
+def device_inputs_e2e(ranks, cfg, B, dev, Ke):
+    """Production flow when the head runs on this GPU: raw level tensors are already in HBM, the
+    fused path (KF + K2) turns them into detections and those go D2H into pinned memory -- the timed
+    region includes that copy and the wait for it, every step."""
+    import torch
+    from yolo_lp_b200 import synth
+    from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+    levels = synth.synth_levels(B, cfg["img"], cfg["img"], dev, seed=cfg["seed"])
+    plans = [PostprocessPlan(levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
+    pipe = PostprocessPipeline(plans)
+    out_host = [torch.empty(tuple(p.out.shape), dtype=torch.float32, pin_memory=True) for p in plans]
+    cnt_host = [torch.empty((B,), dtype=torch.int32, pin_memory=True) for p in plans]
+    copied = [torch.cuda.Event() for _ in plans]
+
+    def step():
+        slot, out, counts = pipe.submit(cfg["conf"], cfg["iou"])
+        with torch.cuda.stream(pipe.s_nms):
+            cnt_host[slot].copy_(counts, non_blocking=True)
+            out_host[slot].copy_(out, non_blocking=True)
+            copied[slot].record(pipe.s_nms)
+        return slot
+
+    pipe.start()
+    for _ in range(4):
+        step()
+    pipe.finish()
+    ranks.barrier()
+    t0 = time.perf_counter()
+    pipe.start()
+    prev = None
+    for _ in range(Ke):
+        slot = step()
+        if prev is not None:
+            copied[prev].synchronize()      # the host consumes batch i-1 while batch i is in flight
+        prev = slot
+    copied[prev].synchronize()
+    pipe.finish()
+    torch.cuda.synchronize(dev)
+    ms = ranks.max((time.perf_counter() - t0) * 1e3) / Ke
+    d2h = out_host[0].numel() * 4 + cnt_host[0].numel() * 4
+    return {"value": ranks.world * B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": Ke, "h2d_bytes_per_step": 0,
+            "d2h_bytes_per_step": d2h, "detections_per_image": float(cnt_host[prev].float().mean()),
+            "api": "PostprocessPipeline.submit (lp_detect_pipelined_f32) on device-resident level tensors + pinned D2H of "
+                   "out[B,max_det,28] and counts[B], host waits for every batch"}
+
+
 # --------------------------------------------------------------------------------------------- side rows
+def other_config(ranks, cid, B_local, first, dev, peak, K, tile_from=None):
+    """Pipelined device-resident throughput (graph of K steps) and K1's roofline for another
+    BASELINE config on every rank: cfg3 strong scaling, cfg5 (1280^2), cfg4 (dense eval)."""
+    import torch
+    from yolo_lp_b200 import synth
+    from yolo_lp_b200.nms import NmsPipeline
+    cfg = dict(synth.CONFIGS[cid])
+    unique = min(B_local, tile_from or B_local)
+    host = synth.synth_head(unique, cfg["A"], cfg["img"], cfg["n_plates"], cfg["n_pos"], cfg["seed"], first_index=first)
+    pred = host.to(dev)
+    if unique < B_local:      # large single-GPU shards: the first `unique` images repeated (same work per image)
+        pred = pred.repeat((B_local + unique - 1) // unique, 1, 1)[:B_local].contiguous()
+    conf, iou = cfg["conf"], cfg["iou"]
+    leg = graph_leg(ranks, lambda: NmsPipeline(B_local, cfg["A"], cfg["max_det"], dev),
+                    lambda p, k: p.capture(pred, conf, iou, k), K, 3, B_local)
+    filt = fenced_k1(NmsPipeline(B_local, cfg["A"], cfg["max_det"], dev), pred, conf, iou, 6)
+    counts = leg["graphed"].pipe.plans[0].counts
+    bytes_ = B_local * cfg["A"] * 1160
+    avg = sum(filt) / len(filt)
+    res = {"workload": NAMES[cid], "images_per_gpu": B_local, "global_batch": B_local * ranks.world,
+           "value": ranks.world * B_local / leg["ms_per_step"] * 1e3, "unit": UNIT, "ms_per_step": leg["ms_per_step"], "steps": K,
+           "k1_avg_launch_ms": avg, "k1_frac_of_hbm_peak": bytes_ / avg / 1e6 / peak, "k1_timed_launches": len(filt),
+           "detections_per_image": float(counts.float().mean())}
+    if unique < B_local:
+        res["note"] = f"{unique} seeded images repeated to fill the {B_local}-image shard"
+    del leg, pred
+    torch.cuda.empty_cache()
+    return res
+
+
 def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     """SURVEY 8 rows next to the headline path, on the same shape: the Detect eval-tail decode kernel
     (raw level tensors -> [B,A,290]) and the fused path (raw level tensors -> detections).  Synthetic
@@ -266,46 +543,26 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
     # KF alone, on the CTA count the serial entry uses (#SMs - #SMs/6); the stage entry on its own
     # would leave one SM per image free for an overlapping K2, which is what the pipelined leg measures
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    _abi.call("lp_tune", 0, sms - min(B, sms // 6))
-    try:
-        t_kf = timed(lambda: plans[0].run_filter(conf))
-    finally:
-        _abi.call("lp_tune", 0, 0)
+    plans[0].opts = _abi.opts(filter_ctas=sms - min(B, sms // 6))
+    t_kf = timed(lambda: plans[0].run_filter(conf))
+    plans[0].opts = None
     t_serial = timed(lambda: plans[0].run(conf, iou))
-    pipe = PostprocessPipeline(plans)
-
-    def burst():
-        pipe.start()
-        for _ in range(K):
-            pipe.submit(conf, iou)
-        pipe.finish()
-    burst()
-    torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    burst()
-    b.record()
-    torch.cuda.synchronize(dev)
-    t_pipe = a.elapsed_time(b) / K
+    ranks1 = Ranks(1, dev)
+    leg = graph_leg(ranks1, lambda: PostprocessPipeline(plans), lambda p, k: p.capture(conf, iou, k), K, 5, B)
+    t_pipe = leg["ms_per_step"]
     dec_bytes, kf_bytes = B * A * (289 + 290) * 4, B * A * 277 * 4
     # the same fused path on fp16 level tensors (model.half()): lp_detect_postprocess_f16 / _pipelined_f16
     half_levels = [{k: v.half() for k, v in lv.items()} for lv in levels]
-    del dec, plans, pipe, levels
+    del dec, plans, leg, levels
     plans = [PostprocessPlan(half_levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
     fused_half = None
     if plans[0].half:
         t_serial_h = timed(lambda: plans[0].run(conf, iou))
-        pipe = PostprocessPipeline(plans)
-        burst()
-        torch.cuda.synchronize(dev)
-        a.record()
-        burst()
-        b.record()
-        torch.cuda.synchronize(dev)
+        leg = graph_leg(ranks1, lambda: PostprocessPipeline(plans), lambda p, k: p.capture(conf, iou, k), K, 5, B)
         fused_half = {"what": "the fused path on fp16 level tensors (lp_detect_postprocess_f16): exact upcast on load",
-                      "serial_ms_per_step": t_serial_h, "pipelined_ms_per_step": a.elapsed_time(b) / K,
-                      "images_per_s_pipelined": B / (a.elapsed_time(b) / K) * 1e3}
-        del pipe
+                      "serial_ms_per_step": t_serial_h, "pipelined_ms_per_step": leg["ms_per_step"],
+                      "images_per_s_pipelined": B / leg["ms_per_step"] * 1e3}
+        del leg
     del plans, half_levels
     torch.cuda.empty_cache()
     return {
@@ -319,34 +576,22 @@ def side_measurements(cfg, B, dev, peak, conf, iou, K=50):
                        "images_per_s_pipelined": B / t_pipe * 1e3, "steps": K}}
 
 
-def half_measurements(cfg, B, dev, peak, conf, iou, pred, host_pred, counts32):
+def half_measurements(cfg, B, dev, peak, conf, iou, pred, host_pred):
     """the same workload with the head tensor stored as fp16 (the reference's
     --half mode) and read natively (exact upcast on load, fp32 arithmetic).  Informational: the graded
     metric is the fp32 line.  Device-resident pipelined throughput, K1's roofline on the halved bytes,
     and the host-buffer end-to-end rate (half the PCIe bytes)."""
-    import time
     import torch
     from yolo_lp_b200.nms import NmsPipeline, NmsPlan, non_max_suppression
     A, max_det, K = cfg["A"], cfg["max_det"], 100
     ph = pred.half()
-    pipe = NmsPipeline(B, A, max_det, dev)
-
-    def burst():
-        pipe.start()
-        for _ in range(K):
-            pipe.submit(ph, conf, iou)
-        pipe.finish()
-    burst()
-    torch.cuda.synchronize(dev)
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    burst()
-    b.record()
-    torch.cuda.synchronize(dev)
-    t_step = a.elapsed_time(b) / K
+    leg = graph_leg(Ranks(1, dev), lambda: NmsPipeline(B, A, max_det, dev), lambda p, k: p.capture(ph, conf, iou, k), K, 5, B)
+    t_step = leg["ms_per_step"]
+    del leg
     plan = NmsPlan(B, A, max_det, dev)
     for _ in range(5):
         plan.run_filter(ph, conf)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(K):
         plan.run_filter(ph, conf)
@@ -364,7 +609,7 @@ def half_measurements(cfg, B, dev, peak, conf, iou, pred, host_pred, counts32):
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) * 1e3 / Ke
     k1_bytes = B * A * 580
-    del pipe, plan, ph, host_h
+    del plan, ph, host_h
     torch.cuda.empty_cache()
     return {"what": "fp16 head tensor [B,A,290] (reference --half mode), upcast exactly on load; results == fp32 path on pred.float()",
             "kernel": "lp::filter_half_kernel", "images_per_s_pipelined": B / t_step * 1e3, "pipelined_ms_per_step": t_step,
@@ -396,6 +641,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    ranks = Ranks(world, dev)
 
     cfg, name = workload(args.config)
     B = cfg["B"] if args.config != 3 else 32      # per-GPU shard; config 3 is the 8-GPU aggregate of config 2's shape
@@ -407,76 +653,42 @@ def run_ours(args):
     plan = NmsPlan(B, cfg["A"], cfg["max_det"], dev)
     conf, iou = cfg["conf"], cfg["iou"]
     K, W = args.steps, max(3, args.warmup)
+    in_l2 = B * cfg["A"] * 1160 <= 126e6
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- device-resident leg (headline): K steps through the two-stream pipeline -- K1 (filter) of
-    # step k+1 overlaps K2 (sort/NMS/gather) of step k; CUDA events round every K1 launch
-    pipe = NmsPipeline(B, cfg["A"], cfg["max_det"], dev)
-    pipe.start()
-    for _ in range(W):
-        pipe.submit(pred, conf, iou)
-    pipe.finish()
-    # every TIME_EVERY-th K1 launch is bracketed by timing events.  A timed launch is fenced off from
-    # its neighbours (consecutive K1s otherwise overlap each other's drain and ramp-up, and a bracket
-    # would then measure queueing, not the kernel), which costs ~20 us of bubble per timed launch --
-    # so only a handful of launches of the timed region (one per 32 steps, six at most) are measured this way.
-    n_timed = max(1, min(6, K // 32))
-    TIME_EVERY = max(1, K // n_timed)
-    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(2)] for k in list(range(TIME_EVERY // 2, K, TIME_EVERY))[:n_timed]}   # never step 0: the pipeline is still filling
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(visible_to_physical(local))
-    barrier()
-    with clocks:
-        t_begin.record()
-        pipe.start()
-        for k in range(K):
-            pipe.submit(pred, conf, iou, timing=ev.get(k))
-        pipe.finish()
-        t_end.record()
-        barrier()
-    total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
-    ms_per_step = total_ms / K
-    filt_ms = [e[0].elapsed_time(e[1]) for e in ev.values()]
-    counts = pipe.plans[0].counts.cpu()
-    assert all(torch.equal(pl.counts.cpu(), counts) for pl in pipe.plans)
-    value = world * B / (ms_per_step / 1e3)
-
-    # ---- latency leg: the same K1, K2 strictly one after the other on one stream (no overlap)
-    Kl = min(K, 100)
-    for _ in range(W):
-        plan.run(pred, conf, iou)
-    lv = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(Kl)]
-    barrier()
-    for k in range(Kl):
-        lv[k][0].record()
-        plan.run_filter(pred, conf)
-        lv[k][1].record()
-        plan.run_suppress(pred, iou)
-        lv[k][2].record()
-    barrier()
-    step_ms = [lv[k][0].elapsed_time(lv[k][2]) for k in range(Kl)]
-    lat_filter = sum(lv[k][0].elapsed_time(lv[k][1]) for k in range(Kl)) / Kl
-    lat_nms = sum(lv[k][1].elapsed_time(lv[k][2]) for k in range(Kl)) / Kl
-    assert torch.equal(plan.counts.cpu(), counts), "pipelined and serial paths disagree"
-    cand = plan.candidate_counts().cpu()
-
-    # ---- roofline of the dominant kernel (K1): algorithmic bytes = every row read once + 8 B per survivor
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+    # ---- device-resident leg (headline): the K timed steps are one CUDA-graph launch of the multi-stream
+    # pipeline -- K1 (filter) of step k+1 overlaps K2 (sort / NMS / gather) of step k -- so the GPU
+    # never waits for the host between steps
+    clocks = ClockSampler(visible_to_physical(local))
+    leg = graph_leg(ranks, lambda: NmsPipeline(B, cfg["A"], cfg["max_det"], dev),
+                    lambda p, k: p.capture(pred, conf, iou, k), K, W, B, clocks)
+    ms_per_step = leg["ms_per_step"]
+    value = world * B / (ms_per_step / 1e3)
+    gplans = leg["graphed"].pipe.plans
+    counts = gplans[0].counts.cpu()
+    assert all(torch.equal(pl.counts.cpu(), counts) for pl in gplans)
+
+    # ---- the same pipeline driven step by step from Python, with the clocks sampled over a longer run
+    Kl = max(K, 200)
+    clocks_long = ClockSampler(visible_to_physical(local), period=0.002)
+    epipe = NmsPipeline(B, cfg["A"], cfg["max_det"], dev)
+    with clocks_long:
+        eager_ms, eager_host_us = eager_leg(ranks, epipe, lambda p: p.submit(pred, conf, iou), Kl)
+    assert all(torch.equal(pl.counts.cpu(), counts) for pl in epipe.plans), "graphed and eager pipelines disagree"
+
+    # ---- roofline of the dominant kernel (K1): 8 fenced launches inside the running pipeline
+    filt_ms = fenced_k1(epipe, pred, conf, iou, 8)
+
+    # ---- latency legs (strictly serial batches)
+    latency, main_lat = latency_block(cfg, B, pred, dev, plan, in_l2)
+    assert torch.equal(plan.counts.cpu(), counts), "pipelined and serial paths disagree"
+    cand = plan.candidate_counts().cpu()
+
     algo_bytes = B * cfg["A"] * 1160 + int(cand.sum()) * 8
     filt_avg = sum(filt_ms) / len(filt_ms)
     achieved = algo_bytes / (filt_avg * 1e-3) / 1e9
@@ -487,81 +699,105 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(f"cfg{args.config}", {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    lat_filter, lat_nms = main_lat["filter_avg_ms"], main_lat["nms_avg_ms"]
     roofline = {"kernel": "lp::filter_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": filt_avg,
+                "launch_ms": [round(t, 5) for t in filt_ms],
                 "share_of_step": filt_avg / ms_per_step,
                 "share_of_serial_step": lat_filter / (lat_filter + lat_nms),   # the figure an ncu launch list (serialised) shows
                 "timed_launches": len(filt_ms),
-                "note": "K1 timed inside the pipelined region, K2 of the previous step running concurrently; the timed launches "
-                        "(one per 32 steps, six at most) are fenced off from the neighbouring K1s, which otherwise overlap each other's drain and "
-                        "ramp-up -- hence share_of_step > 1"}
+                "note": "8 K1 launches of a leg that follows the timed region, inside the running pipeline (K2 of the previous "
+                        "step beside them), each fenced off from the neighbouring K1s -- which in the timed region overlap each "
+                        "other's drain and ramp-up, hence share_of_step can exceed 1"
+                        + ("; this workload fits L2, so the launches read from cache" if in_l2 else "")}
 
     # ---- end-to-end leg: public API on a pinned HOST tensor; H2D + kernels + D2H per step
     Ke = args.e2e_steps or max(3, min(K, 20))
-    pipe = host_pipeline(B, cfg["A"], cfg["max_det"])
+    hpipe = host_pipeline(B, cfg["A"], cfg["max_det"])
     for _ in range(3):
         res = non_max_suppression(host_pred, conf, iou, max_det=cfg["max_det"])
-    barrier()
+    ranks.barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
         res = non_max_suppression(host_pred, conf, iou, max_det=cfg["max_det"])
     torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / Ke
+    e2e_ms = ranks.max((time.perf_counter() - t0) * 1e3) / Ke
     assert [int(r.shape[0]) for r in res] == counts.tolist(), "host-buffer path disagrees with the device path"
+    ceiling_gbs = h2d_ceiling(ranks, host_pred, torch.empty_like(pred), max(3, Ke // 2))
+    e2e_gbs = hpipe.h2d_bytes / e2e_ms / 1e6
     e2e = {"value": world * B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": Ke,
-           "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+           "h2d_bytes_per_step": hpipe.h2d_bytes, "d2h_bytes_per_step": hpipe.d2h_bytes,
+           "h2d_gbs_per_rank": e2e_gbs, "h2d_ceiling_gbs_per_rank": ceiling_gbs, "frac_of_h2d_ceiling": e2e_gbs / ceiling_gbs,
+           "ceiling": "bare pinned cudaMemcpyAsync of the same tensor on every rank at once (slowest rank)",
            "api": "yolo_lp_b200.non_max_suppression(cpu pinned tensor) -> lp_nms_f32 per 48 MiB chunk"}
-    barrier()
+    ranks.barrier()
+    e2e_dev = device_inputs_e2e(ranks, cfg, B, dev, max(Ke, 50))
+    ranks.barrier()
 
-    extras = None
-    if not args.no_extras and rank == 0:
-        extras = side_measurements(cfg, B, dev, peak, conf, iou)
-        extras["half_head_tensor"] = half_measurements(cfg, B, dev, peak, conf, iou, pred, host_pred, counts)
-    barrier()
+    extras = {}
+    if not args.no_extras:
+        Kx = min(max(K, 20), 100)
+        # BASELINE config 3: the 256-image batch image-sharded over the ranks (strong scaling: 256/N per GPU)
+        extras["cfg3_strong"] = other_config(ranks, 3, 256 // world, rank * (256 // world), dev, peak, Kx, tile_from=32)
+        extras["cfg3_strong"]["scaling"] = "strong: global batch 256 fixed, 256/N images per GPU"
+        # BASELINE config 5: 1280x1280, 32 images per GPU (weak)
+        extras["cfg5_1280"] = other_config(ranks, 5, 32, rank * 32, dev, peak, min(Kx, 40), tile_from=8)
+        if world == 1:
+            extras["cfg4_dense_eval"] = other_config(ranks, 4, 64, 0, dev, peak, min(Kx, 50), tile_from=16)
+            extras.update(side_measurements(cfg, B, dev, peak, conf, iou))
+            extras["half_head_tensor"] = half_measurements(cfg, B, dev, peak, conf, iou, pred, host_pred)
+    ranks.barrier()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_block(cfg, name, world, B),
-                "pipeline": "K1 alternates between 2 streams, K2 on a third, 2 workspaces: K1 of step k+1 overlaps K2 of step k "
-                            "and the drain of K1 of step k",
-                "p50_batch_latency_ms": statistics.median(step_ms), "p95_batch_latency_ms": sorted(step_ms)[int(0.95 * (Kl - 1))],
+                "pipeline": "the K timed steps are one CUDA graph (NmsPipeline.capture): K1 alternates between 2 streams, K2 on a "
+                            "third, 2 workspaces -- K1 of step k+1 overlaps K2 of step k and the drain of K1 of step k",
+                "warmup_steps_run": leg["warmup_steps_run"],
+                "host_submit_us_per_step": leg["host_submit_us_per_step"],
+                "eager": {"ms_per_step": eager_ms, "value": world * B / eager_ms * 1e3, "host_submit_us_per_step": eager_host_us,
+                          "steps": Kl, "what": "the same pipeline submitted step by step from Python (lp_nms_pipelined_f32 per step)"},
+                "p50_batch_latency_ms": main_lat["p50_ms"], "p95_batch_latency_ms": main_lat["p95_ms"],
                 "serial_stage_ms": {"filter_avg": lat_filter, "nms_avg": lat_nms},
+                "latency": latency,
                 "detections_per_image": sum(counts.tolist()) / B, "candidates_per_image": float(cand.sum()) / B,
-                "roofline": roofline, "e2e": e2e, "clocks": clocks.summary(), "extras": extras,
+                "roofline": roofline, "e2e": e2e, "e2e_device_inputs": e2e_dev,
+                "clocks": dict(clocks.summary(), sustained=clocks_long.summary()), "extras": extras or None,
                 "gpu_launches": K * NmsPlan.KERNELS_PER_CALL}
         if world == 1 and not args.no_cpu_baseline:
             restore_affinity(prev_affinity)
             use_all_host_threads()
+            fn, kind, what = reference_callable()
             sample = cpu_sample(cfg, cpu_sample_size(args.config))
-            cpu_pass(sample, cfg)                      # warm-up
+            cpu_pass(fn, sample, cfg)                  # warm-up
             spent, images, passes = 0.0, 0, 0
             while spent < 10.0 and passes < 1000:     # ~10 s of CPU work on the bounded sample
-                dt, n = cpu_pass(sample, cfg)
+                dt, n = cpu_pass(fn, sample, cfg)
                 spent, images, passes = spent + dt, images + n, passes + 1
             line["cpu_baseline"] = {
-                "value": images / spent, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "value": images / spent, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                 "host_cpus": os.cpu_count(),
                 "sample": f"{passes} passes over {sample.shape[0]} images of {name} ({spent:.1f} s), "
-                          f"{CPU_CHUNK}-image calls, torch CPU port of nms.py + torchvision.ops.nms"}
+                          f"{CPU_CHUNK}-image calls, {what}"}
             # second baseline of SURVEY 8-d: the reference's own GPU route (what tools/infer.py --device 0
-            # does today) -- the same port on CUDA tensors: ~45 ATen launches per image + torchvision's
+            # does today) -- the same function on CUDA tensors: ~45 ATen launches per image + torchvision's
             # generic CUDA nms kernel.  Not used for parity (it is not bit-identical to the CPU kernel).
             try:
                 gsample = sample.to(dev)
-                cpu_pass(gsample, cfg)
+                cpu_pass(fn, gsample, cfg)
                 torch.cuda.synchronize(dev)
                 t0 = time.perf_counter()
                 n_img = 0
                 for _ in range(3):
-                    _dt, n = cpu_pass(gsample, cfg)
+                    _dt, n = cpu_pass(fn, gsample, cfg)
                     n_img += n
                 torch.cuda.synchronize(dev)
                 line["reference_cuda_route"] = {
                     "value": n_img / (time.perf_counter() - t0), "unit": UNIT,
-                    "what": "torch port of the reference on CUDA tensors of the same B200 (ATen kernels + "
-                            "torchvision CUDA nms), input clone included, 8-image calls"}
+                    "what": f"{what} on CUDA tensors of the same B200 (ATen kernels + torchvision CUDA nms), "
+                            "input clone included, 8-image calls"}
             except Exception as exc:  # torchvision CUDA ops missing etc.: report, do not fail the bench
                 line["reference_cuda_route"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line), file=JSON_OUT, flush=True)

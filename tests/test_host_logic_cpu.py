@@ -111,7 +111,7 @@ def test_two_rank_gloo_gather_preserves_image_order():
 
 
 def test_bench_reference_arm_prints_one_json_line_on_cpu():
-    """`bench.py --impl reference` is CPU-only (the oracle's torch port on all host threads): it must run
+    """`bench.py --impl reference` is CPU-only (the staged reference, else its torch port, on all host threads): it must run
     without a GPU and put exactly one JSON line with the contract's keys on stdout."""
     import json
     import subprocess
@@ -125,6 +125,7 @@ def test_bench_reference_arm_prints_one_json_line_on_cpu():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "post-proc images/sec" and d["unit"] == "images/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import stage_ref
+    assert d["cpu_baseline"]["kind"] == ("reference" if stage_ref.is_staged() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"].startswith("cfg2")

@@ -256,6 +256,12 @@ class PostprocessPipeline:
             cur.wait_stream(sf)
         cur.wait_stream(self.s_nms)
 
+    def capture(self, conf_thres, iou_thres, steps: int):
+        """``steps`` pipelined steps as one CUDA graph (yolo_lp_b200.nms.GraphedSteps); this pipeline
+        then belongs to the graph."""
+        from .nms import GraphedSteps
+        return GraphedSteps(self, lambda p: p.submit(conf_thres, iou_thres), steps)
+
 
 def detect_postprocess(levels, strides=(8, 16, 32), conf_thres=0.25, iou_thres=0.45, max_det=300):
     """``non_max_suppression(Detect.forward(x))`` from the raw prediction-conv outputs in two

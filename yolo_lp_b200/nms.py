@@ -187,6 +187,54 @@ class NmsPipeline:
             cur.wait_stream(sf)
         cur.wait_stream(self.s_nms)
 
+    def capture(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, steps: int) -> "GraphedSteps":
+        """``steps`` pipelined steps over ``pred`` as one CUDA graph (see :class:`GraphedSteps`); this
+        pipeline then belongs to the graph."""
+        return GraphedSteps(self, lambda p: p.submit(pred, conf_thres, iou_thres), steps)
+
+
+class GraphedSteps:
+    """``steps`` consecutive pipelined steps captured ONCE into a CUDA graph and replayed with a
+    single launch: the steady state of :class:`NmsPipeline` / ``PostprocessPipeline`` (K1 / KF
+    alternating between the filter streams, K2 on the NMS stream, the events between them) becomes
+    graph edges, so the GPU never waits for the host to submit the next step -- the per-step host
+    cost (one Python -> ctypes call and ~6 CUDA API calls) is what capped 8-GPU scaling in round 1.
+
+    The pipeline passed in is private to the graph from then on (its events were recorded under
+    capture).  ``submit_one(pipe)`` must enqueue exactly one step on it.  Results of the last
+    ``depth`` steps are in ``pipe.plans[i].out / .counts`` after a replay.
+    """
+
+    def __init__(self, pipe, submit_one, steps: int):
+        self.pipe, self.steps = pipe, int(steps)
+        dev = pipe.device
+        for plan in pipe.plans:      # no event recorded outside the capture may be waited on inside it
+            plan.armed = False
+        pipe.n = 0
+        with torch.cuda.device(dev):
+            # once eagerly: lazy per-device initialisation (kernel attributes, tensor-map encoder) must
+            # not happen under capture
+            pipe.start()
+            submit_one(pipe)
+            pipe.finish()
+            torch.cuda.synchronize(dev)
+            for plan in pipe.plans:
+                plan.armed = False
+            pipe.n = 0
+            self.graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(dev)
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode="thread_local"):
+                pipe.start()
+                for _ in range(self.steps):
+                    submit_one(pipe)
+                pipe.finish()
+        for plan in pipe.plans:      # eager use of these plans afterwards starts from a memset again
+            plan.armed = False
+
+    def launch(self):
+        """Replay the ``steps`` steps on the current stream (one cudaGraphLaunch)."""
+        self.graph.replay()
+
 
 _plans: dict = {}
 
