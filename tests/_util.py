@@ -83,3 +83,28 @@ def iou_band_pairs(iou, n=6000):
     pred[:, 0, 13:] = 0.9      # the first box wins the order
     pred[:, 1, 13:] = 0.8
     return torch.from_numpy(pred)
+
+
+def maxnms_input(A=33600, img=1280, seed=20261019):
+    """One ``[A, 290]`` image in which EVERY anchor passes ``conf_thres = 0`` and all ``A`` scores are
+    distinct -- so the reference's more-than-30000-candidates cut (nms.py:115-116, an unstable argsort)
+    has exactly one answer.  Each group carries one class at ``v = k / 65536`` (k distinct per anchor)
+    and zeros elsewhere: sums of up to eight equal multiples of 2^-16 are exact, so both 8-term means
+    equal ``v`` exactly.  numpy's PCG64 only, so the bits are the same everywhere (pinned by SHA-256)."""
+    rng = np.random.default_rng(seed)
+    x = np.zeros((A, 290), np.float32)
+    centres = rng.uniform(0, img, (192, 2))
+    which = rng.integers(0, 192, A)
+    cxy = centres[which] + rng.normal(0, 14.0, (A, 2))
+    wh = rng.uniform(20, 90, (A, 2))
+    x[:, 0:2], x[:, 2:4], x[:, 4] = cxy.astype(np.float32), wh.astype(np.float32), 1.0
+    x[:, 5:13] = (np.tile(cxy, 4) + (rng.uniform(size=(A, 8)) - 0.5) * np.tile(wh, 4)).astype(np.float32)
+    k = rng.permutation(np.arange(6000, 6000 + A))          # distinct, 8 * k < 2^24
+    v = (k / 65536.0).astype(np.float32)
+    widths = (31, 24, 37, 37, 37, 37, 37, 37)
+    col = 13
+    for w in widths:
+        j = rng.integers(0, w, A)
+        x[np.arange(A), col + j] = v
+        col += w
+    return torch.from_numpy(x)

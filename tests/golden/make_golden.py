@@ -342,7 +342,30 @@ def make_iou_band():
     save("iou_band", thresholds=np.array(IOU_BAND_THRESHOLDS, np.float64), **out)
 
 
+def make_maxnms():
+    """More than max_nms = 30000 candidates at the default (nms.py:62,115-116): A = 33600, every anchor
+    passes conf 0, distinct scores (tests/_util.maxnms_input) -- the reference's cut then has one answer."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    from _util import maxnms_input
+    x = maxnms_input()
+    arrays = {"sha256": np.array(synth.sha256_of(x))}
+    for tag, iou, max_det in (("a", 0.45, 300), ("b", 0.9, 1000)):
+        rows = run_ref_nms(x[None], 0.0, iou, max_det)
+        counts, flat = pack_rows(rows)
+        arrays.update({f"iou_{tag}": np.array(iou), f"max_det_{tag}": np.array(max_det), f"counts_{tag}": counts,
+                       f"rows_{tag}": flat})
+        print("   ", tag, "counts", counts.tolist(), "lowest kept score", float(flat[:, 12:20].mean(1).min()))
+    # the cut itself decides this one: nothing suppressed below IoU 0.999 and max_det above the candidate
+    # count, so the reference keeps exactly the 30000 best-scored rows (stored as a digest + the tail)
+    import hashlib
+    rows = run_ref_nms(x[None], 0.0, 0.999, 33600)[0]
+    arrays.update(count_c=np.array(rows.shape[0]), sha256_c=np.array(hashlib.sha256(rows.tobytes()).hexdigest()),
+                  tail_c=rows[-16:].copy(), lowest_c=np.array(rows[:, 12:20].mean(1).min()))
+    print("    c count", rows.shape[0], "lowest kept score", float(rows[:, 12:20].mean(1).min()))
+    save("nms_maxnms_33600", **arrays)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets", "iou_band"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets", "iou_band", "maxnms"]
     for w in which:
         globals()["make_" + w]()

@@ -157,12 +157,11 @@ def test_use_dfl_head_stays_with_the_reference(patched):
 
 
 def test_half_mode_dtype_flow_and_agreement_with_the_reference_cuda_route(ref):
-    """--half (inferer.py:46-50): model.half() on the GPU.  The drop-in keeps the reference's dtype
-    flow (fp16 head tensor, fp16 rows).  Contract: our rows are the fp32 path's on the
-    upcast conv outputs, rounded once -- checked exactly -- and they agree with the reference's own
-    CUDA half route (per-operation half arithmetic, unstable sort) to half precision on the
-    detections both keep."""
-    import yolo_lp_b200 as lp
+    """--half (inferer.py:46-50): model.half() on the GPU.  The reference's head tensor is fp32 even
+    then (fp32 anchors promote dist2bbox / dist2cor and torch.cat promotes the half sigmoids), so its
+    NMS runs in fp32.  The drop-in keeps that flow: box / corner columns are the same fp32 arithmetic
+    on the same half conv outputs -- bit-identical to the reference's CUDA route -- and the class
+    columns are fp32 sigmoids where the reference rounds them to half (<= 2^-11 relative)."""
     from yolo_lp_b200 import patch
     B, H, W, conf = 2, 640, 640, 0.3
     head = ref.build_head(CH, rerandomise=True, seed=3).to(DEV).half()
@@ -176,20 +175,17 @@ def test_half_mode_dtype_flow_and_agreement_with_the_reference_cuda_route(ref):
             our_rows = ref.nms.non_max_suppression(our_head, conf, 0.45, max_det=300)
         finally:
             patch.uninstall()
-    assert our_head.dtype == their_head.dtype == torch.float16 and our_head.shape == their_head.shape
-    assert all(r.dtype == torch.float16 and r.is_cuda for r in our_rows)
-    # exactly the contract: fp32 kernels on the upcast tensor, rounded once
-    up = lp.non_max_suppression(our_head.float(), conf, 0.45, max_det=300)
-    for i in range(B):
-        assert torch.equal(our_rows[i], up[i].half())
-    # and close to the reference's half route: head tensor to half precision ...
-    np.testing.assert_allclose(our_head.float().cpu().numpy(), their_head.float().cpu().numpy(), rtol=4e-3, atol=0.3)
-    # ... and most kept detections in common (matched by box within 2 px)
+    assert our_head.dtype == their_head.dtype == torch.float32 and our_head.shape == their_head.shape
+    assert all(r.dtype == torch.float32 and r.is_cuda for r in our_rows) and all(r.dtype == torch.float32 for r in their_rows)
+    a, b = our_head.cpu().numpy(), their_head.cpu().numpy()
+    assert np.array_equal(a[..., :13].view(np.uint32), b[..., :13].view(np.uint32)), "box / obj / corner columns differ"
+    np.testing.assert_allclose(a[..., 13:], b[..., 13:], rtol=6e-4, atol=1e-7)     # half rounding of the sigmoid
+    # most kept detections in common with the reference's route (scores differ by the half rounding)
     common = total = 0
     for i in range(B):
-        a, b = our_rows[i].float().cpu().numpy(), their_rows[i].float().cpu().numpy()
-        total += max(a.shape[0], b.shape[0])
-        for r in a:
-            if b.shape[0] and np.abs(b[:, :4] - r[:4]).max(1).min() <= 2.0:
+        x, y = our_rows[i].cpu().numpy(), their_rows[i].cpu().numpy()
+        total += max(x.shape[0], y.shape[0])
+        for r in x:
+            if y.shape[0] and np.abs(y[:, :4] - r[:4]).max(1).min() == 0.0:
                 common += 1
-    assert total > 0 and common >= 0.8 * total, f"only {common} of {total} detections in common with the reference's half route"
+    assert total > 0 and common >= 0.9 * total, f"only {common} of {total} detections in common with the reference's half route"

@@ -53,6 +53,26 @@ def test_torch_port(name):
         assert_rows_equal(a.numpy(), w, f"{name}[{b}]")
 
 
+def test_more_than_max_nms_candidates_golden():
+    """nms.py:115-116 at the default max_nms = 30000: numpy oracle and torch port against the reference's
+    output on 33600 passing anchors with distinct scores (tests/_util.maxnms_input)."""
+    import hashlib
+    from _util import maxnms_input
+    from yolo_lp_b200 import synth
+    g = golden("nms_maxnms_33600")
+    x = maxnms_input()
+    assert synth.sha256_of(x) == str(g["sha256"]), "numpy generator is not bit-reproducible on this host"
+    for tag in ("a", "b"):
+        iou, max_det = float(g[f"iou_{tag}"]), int(g[f"max_det_{tag}"])
+        got = lp_oracle.non_max_suppression(x[None].numpy(), 0.0, iou, max_det=max_det)
+        assert_rows_equal(got[0], g[f"rows_{tag}"], f"numpy oracle {tag}")
+        tp = torch_port.non_max_suppression(x[None].clone(), 0.0, iou, max_det=max_det)
+        assert_rows_equal(tp[0].numpy(), g[f"rows_{tag}"], f"torch port {tag}")
+    rows = torch_port.non_max_suppression(x[None].clone(), 0.0, 0.999, max_det=33600)[0].numpy()
+    assert rows.shape[0] == int(g["count_c"]) == 30000 and np.array_equal(rows[-16:], g["tail_c"])
+    assert hashlib.sha256(rows.tobytes()).hexdigest() == str(g["sha256_c"])
+
+
 def _levels(g):
     return [{k: g[f"l{l}_{k}"] for k in ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5", "reg", "cor")}
             for l in range(3)]

@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblpnms.so")
+# LPNMS_LIB: another build of the same ABI (the -DLP_KF_ASSERT library of tests/test_gpu_kf_assert.py)
+LIB_PATH = os.environ.get("LPNMS_LIB") or os.path.join(HERE, "liblpnms.so")
 
 ROW = 290
 OUT = 28

@@ -74,11 +74,18 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in dependencies())
 
 
-def build(force: bool = False, verbose: bool = False, lib: str = LIB) -> str:
+ASSERT_LIB = os.path.join(HERE, "liblpnms_kfassert.so")   # the same library with -DLP_KF_ASSERT (see fused_tma.cu)
+
+
+def build_assert_lib() -> str:
+    return build(force=True, lib=ASSERT_LIB, extra=["-DLP_KF_ASSERT"])
+
+
+def build(force: bool = False, verbose: bool = False, lib: str = LIB, extra: list | None = None) -> str:
     """Compile ``liblpnms.so`` if missing or older than its sources; return its path."""
     if not force and lib == LIB and not is_stale():
         return lib
-    nvcc, extra = nvcc_path(), extra_flags()
+    nvcc, extra = nvcc_path(), extra_flags() + list(extra or [])
     os.makedirs(OBJ, exist_ok=True)
     tag = "" if lib == LIB else "." + os.path.basename(lib)
 

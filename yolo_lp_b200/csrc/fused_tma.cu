@@ -147,6 +147,20 @@ __device__ __forceinline__ void locate(const LevelsFilterParams& p, int tile, in
 #define LP_PF_OUT() do { } while (0)
 #endif
 
+// -DLP_KF_ASSERT builds (liblpnms_kfassert.so, tests/test_gpu_kf_assert.py) tag every hand-off with the
+// tile sequence number it belongs to and trap on a mismatch -- the three schedule-dependent bugs listed
+// above were each a warp acting on a slot in the wrong PHASE, which only showed as rare wrong keys:
+//   tag_issued[s]    producer, before the loads of tile `it` are issued into slot s
+//   tag_scanned[s][w] scanner w, with its results of tile `it`
+//   tag_released[s]  finisher, before it hands slot s back
+// checks: scanner after `full` (the data in the slot is tile it's), finisher after the slot barrier (all
+// sixteen results are tile it's), producer after `empty` (the tile it overwrites, it - RING, was released).
+#ifdef LP_KF_ASSERT
+#define LP_KA(cond) do { if (!(cond)) __trap(); } while (0)
+#else
+#define LP_KA(cond) do { } while (0)
+#endif
+
 template <bool kHalf>
 __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const LevelsFilterParams p,
                                                                             const __grid_constant__ DecodeMaps maps) {
@@ -161,6 +175,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
     int* part_a = reinterpret_cast<int*>(part_p + KT_RING * KT_PART_WORDS);      // ... its first index in the group
     uint64_t* full = reinterpret_cast<uint64_t*>(part_a + KT_RING * KT_PART_WORDS);
     uint64_t* empty = full + KT_RING;
+#ifdef LP_KF_ASSERT
+    __shared__ volatile int tag_issued[KT_RING], tag_released[KT_RING], tag_scanned[KT_RING][KT_SCANNERS];
+    if (threadIdx.x < KT_RING) { tag_issued[threadIdx.x] = -1; tag_released[threadIdx.x] = -1; }
+    if (threadIdx.x < KT_RING * KT_SCANNERS) tag_scanned[threadIdx.x / KT_SCANNERS][threadIdx.x % KT_SCANNERS] = -1;
+#endif
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -187,6 +206,12 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             locate(p, first + it * step, b, l, p0);
             LP_PF(0);
             if (use > 0) mbar_wait_relaxed(&empty[s], (use - 1) & 1);
+#ifdef LP_KF_ASSERT
+            LP_KA(tag_released[s] == (use > 0 ? it - KT_RING : -1));   // the slot's previous tile was handed back, no other
+            LP_KA(tag_issued[s] == (use > 0 ? it - KT_RING : -1));
+            tag_issued[s] = it;
+            __threadfence_block();
+#endif
             LP_PF(1);
             T* stage = stage0 + s * STAGE_ELEMS;
             fence_proxy_async_smem();   // the stage was last read through the generic proxy
@@ -210,6 +235,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             // through plain overtaking, then, with an `empty`-phase wait in front, through the parity
             // aliasing described at the producers.)
             slot_wait(s);
+#ifdef LP_KF_ASSERT
+            if (lane < KT_SCANNERS) LP_KA(tag_scanned[s][lane] == it);   // every scanner's result is THIS tile's
+            LP_KA(tag_issued[s] == it);
+#endif
             LP_PF(1);               // all sixteen half-group results of tile `it` are in the exchange buffer
             float c[NGROUP];
             unsigned long long args = 0;
@@ -225,6 +254,9 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
                 args |= (unsigned long long)arg << (6 * g);
             }
             __syncwarp();               // every lane has its copy: the slot (stage + exchange) may be refilled
+#ifdef LP_KF_ASSERT
+            if (lane == 0) { tag_released[s] = it; __threadfence_block(); }
+#endif
             if (lane == 0) mbar_arrive(&empty[s]);
             //   score: sigmoid of the maximum logit == maximum of the sigmoids (monotone device sigmoid);
             //   tie:   arg is the first index of the maximum LOGIT; the reference takes the first index of
@@ -247,6 +279,10 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             LP_PF(0);
             if (lane == 0) mbar_wait(&full[s], (it / KT_RING) & 1);
             __syncwarp();
+#ifdef LP_KF_ASSERT
+            LP_KA(tag_issued[s] == it);                                  // the slot holds THIS tile's planes
+            LP_KA(tag_scanned[s][warp] == (it >= KT_RING ? it - KT_RING : -1));
+#endif
             LP_PF(1);               // a real barrier for the compiler too: no stage read may move above it
             const int g = warp >> 1, half = warp & 1;
             const T* col0 = stage0 + s * STAGE_ELEMS + stage_rows[g] * DEC_TILE + lane;
@@ -259,6 +295,11 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
             part_b[q] = best;
             part_p[q] = before;
             part_a[q] = arg;
+#ifdef LP_KF_ASSERT
+            LP_KA(tag_issued[s] == it);                                  // ... and still does after the scan
+            __syncwarp();
+            if (lane == 0) { tag_scanned[s][warp] = it; __threadfence_block(); }
+#endif
             slot_arrive(s);             // non-blocking
             LP_PF(2);
         }

@@ -302,11 +302,12 @@ def detect_forward_eval(detect, x):
         lv["reg"] = detect.reg_preds[i](reg_feat)
         lv["cor"] = detect.cor_preds[i](reg_feat)
         levels.append(lv)
-    out = detect_decode(levels, [float(s) for s in detect.stride])
-    # model.half() (inferer.py:46-50): the reference's head tensor is fp16, and a drop-in keeps the dtype
-    # flow -- the decode itself upcasts the conv outputs exactly and computes in fp32 (one rounding at the
-    # end instead of the reference's per-operation half arithmetic)
-    return out.half() if x[0].dtype == torch.float16 else out
+    # model.half() (inferer.py:46-50): the reference's head tensor is fp32 even then -- its anchors are
+    # fp32, so dist2bbox / dist2cor promote (general.py:29-66) and torch.cat promotes the half sigmoids
+    # with them (effidehead.py:288-301).  The decode upcasts the half conv outputs exactly and computes
+    # in fp32, which IS the reference's arithmetic for the box / corner columns; the class columns are
+    # fp32 sigmoids where the reference's are sigmoids rounded to half.
+    return detect_decode(levels, [float(s) for s in detect.stride])
 
 
 def detect_forward_nms(detect, x, conf_thres=0.25, iou_thres=0.45, max_det=300):
