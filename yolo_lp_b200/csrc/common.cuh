@@ -115,14 +115,18 @@ __device__ __forceinline__ float decode_corner(int k, float ax, float ay, float 
 // Verified monotone non-decreasing over every finite fp32 input (tools/sigmoid_monotone.py), which
 // is what makes max_j sigmoid(x_j) == sigmoid(max_j x_j) exact in the fused path.
 static __device__ __noinline__ float sigmoid_slow(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
-__device__ __forceinline__ float sigmoid_f32(float x) {
+// the SFU route alone (valid for |x| <= 30), branch-free
+__device__ __forceinline__ float sigmoid_sfu(float x) {
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(x, -1.4426950408889634f)));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fadd_rn(1.0f, e)));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_f32(float x) {
+    float r = sigmoid_sfu(x);
     if (fabsf(x) > 30.0f) r = sigmoid_slow(x);
     return r;
 }
-
 // Inferer.rescale on one coordinate (inferer.py:210-225) + optional caller .round() (:100)
 __device__ __forceinline__ float rescale_coord(float v, float pad, float ratio, float hi, int do_round) {
     v = __fdiv_rn(__fsub_rn(v, pad), ratio);
@@ -161,6 +165,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // warps that do the work
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+}
+// Warp-collective wait with ONE poller: lane 0 polls, a vote ends the loop and -- the point -- leaves the
+// warp converged.  `if (lane == 0) mbar_wait(...); __syncwarp();` does not: WARPSYNC synchronises the
+// lanes but they keep executing as two groups afterwards (ncu on round 2's KF: lane 0 ran whole tiles
+// apart from lanes 1-31, avg 20 threads per instruction, every later ballot / shuffle on the slow
+// divergent path).  All 32 lanes must call it.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, int lane) {
+    for (;;) {
+        bool ok = false;
+        if (lane == 0) ok = mbar_try_wait(bar, parity);
+        if (__any_sync(0xffffffffu, ok)) break;
+    }
 }
 // generic-proxy reads of a buffer must be ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -135,13 +135,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tma_kernel(const DecodeP
             const TileInfo t = w.info(p);
             const DecodeLevel& lv = p.lv[t.l];
             LP_PF(3);
-            // one poller per warp: 512 threads spinning on try_wait slowed the arrivals on the same barriers
-            if (lane == 0) {
-                if (it >= DT_OUTS) mbar_wait(&oempty[o], (it / DT_OUTS - 1) & 1);
-                LP_PF(0);
-                mbar_wait(&full[s], (it / DT_STAGES) & 1);
-            }
-            __syncwarp();
+            // one poller per warp (512 threads spinning on try_wait slowed the arrivals on the same barriers),
+            // through mbar_wait_warp so that the warp is converged again when it starts on the tile
+            if (it >= DT_OUTS) mbar_wait_warp(&oempty[o], (it / DT_OUTS - 1) & 1, lane);
+            LP_PF(0);
+            mbar_wait_warp(&full[s], (it / DT_STAGES) & 1, lane);
             LP_PF(1);
             transpose_tile(stage, outt, t, lv, warp, lane);
             fence_proxy_async_smem();   // generic-proxy writes of outt -> visible to the bulk store

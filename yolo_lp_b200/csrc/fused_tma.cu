@@ -32,6 +32,15 @@
 // The kernel is instantiated for fp32 and for fp16 level tensors (kHalf: FLOAT16 tensor maps, 64-byte
 // stage rows with every group starting on an even row, exact upcast in the scanners and finishers).
 // Tiles are assigned statically (tile = blockIdx.x + it * gridDim.x): every tile costs the same here.
+// Round 2 tried to lift this kernel from 0.80 to 0.90 of the HBM rate and measured four re-designs, all
+// bit-identical and all SLOWER on the cfg2 shape (56 us here): K1's structure -- six warps, each the only
+// producer and consumer of its own stage, maxima-only reduction, argmax recovered for survivors only --
+// 64 us, and 246 us on dense eval thresholds (six warps cannot hide the survivors' work and the ~1000
+// cycles a warp needs to issue eight UTMALDGs); the same with dedicated producer warps 70 us; this
+// kernel with maxima-only scanners and finisher-side argmax recovery 75 us (the finisher then holds the
+// slot ~2000 cycles longer, and five slots is all that fits); this kernel with four producer warps 68 us.
+// What limits it is the time a slot spends NOT loading (issue ~1000 + scan ~860 + hand-offs) against five
+// slots of 35 KB; what did help, mostly on dense tiles (150 -> 127 us), is mbar_wait_warp below.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
 #include <type_traits>
 
@@ -277,8 +286,7 @@ __global__ void __launch_bounds__(KT_THREADS, 1) levels_filter_tma_kernel(const 
         for (int it = 0; it < n_my; ++it) {
             const int s = it % KT_RING;
             LP_PF(0);
-            if (lane == 0) mbar_wait(&full[s], (it / KT_RING) & 1);
-            __syncwarp();
+            mbar_wait_warp(&full[s], (it / KT_RING) & 1, lane);   // one poller, and the warp leaves CONVERGED (common.cuh)
 #ifdef LP_KF_ASSERT
             LP_KA(tag_issued[s] == it);                                  // the slot holds THIS tile's planes
             LP_KA(tag_scanned[s][warp] == (it >= KT_RING ? it - KT_RING : -1));
