@@ -877,3 +877,25 @@ def test_prepare_targets_matches_reference():
     assert len(out) == int(g["bs"])
     for i, o in enumerate(out):
         assert np.array_equal(o.cpu().numpy().view(np.uint32), g[f"out{i}"].view(np.uint32)), i
+
+
+@pytest.mark.parametrize("n,shift", [(400, 4.0), (1500, 4.0), (300, 2.5)])
+def test_long_suppression_chain_takes_the_sequential_pass(n, shift):
+    """A row of equal boxes in which each overlaps its successors a little less: with shift 4 (IoU 0.43 at
+    distance one... 10-wide boxes) the greedy result alternates down the whole list -- every decision
+    depends on the previous one, the worst case for K2's parallel fixed-point rounds (they do not settle
+    within FIXPOINT_ROUNDS and the sequential pass must take over); shift 2.5 makes every box kill its
+    next two.  Kept anchors and rows bit-exact vs the oracle; several windows for n = 1500."""
+    x = torch.zeros((1, n, 290))
+    k = torch.arange(n, dtype=torch.float32)
+    x[0, :, 0] = 100.0 + k * shift          # cx
+    x[0, :, 1] = 50.0
+    x[0, :, 2] = 10.0                        # w: IoU(d) = (10 - d) / (10 + d) for centre distance d
+    x[0, :, 3] = 20.0
+    x[0, :, 4] = 1.0
+    x[0, :, 13:] = (0.9 - 0.0005 * k)[:, None]     # strictly decreasing scores: list order = anchor order
+    want, widx = lp_oracle.non_max_suppression(x.numpy(), 0.1, 0.4, max_det=n, return_index=True)
+    rows, idx = non_max_suppression_with_index(x.to(DEV), 0.1, 0.4, n)
+    assert len(widx[0]) > n // 4
+    assert np.array_equal(idx[0].cpu().numpy(), widx[0])
+    assert_rows_equal(rows[0].cpu().numpy(), want[0], "chain")

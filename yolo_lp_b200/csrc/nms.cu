@@ -28,7 +28,16 @@
 //           are kept, which the reference's truncation keep[:max_det] (nms.py:122-123) makes legal.
 //           (The first version resolved 512-wide windows eagerly, every later candidate against every
 //           alive member of the current chunk: 2-3x the IoU tests and three barriers per step;
-//           cfg2 35 -> 28, cfg4 87 -> 60, cfg5 228 -> 110 thousand cycles for this phase.)
+//           cfg2 35 -> 28, cfg4 87 -> 60, cfg5 228 -> 110 thousand cycles for this phase.
+//           Round 2 measured two "suppression matrix first, resolve after" designs for this phase, both
+//           bit-exact and both slower than the chunk walk's 28 thousand cycles on cfg2: warp per member with
+//           one ballot per 32 predecessors + a 32-members-per-step resolve on one warp, 44 thousand (every
+//           (member, word) item is a ~500-cycle dependent chain of LDS -> IoU -> ballot -> store); and
+//           2-8 threads per member running serial IoU loops + the greedy set as a parallel fixed point,
+//           78 thousand (the lanes of a warp then test unrelated pairs and diverge through the IoU
+//           shortcuts).  The walk does a third of the IoU tests of either and keeps a warp's lanes on one
+//           candidate.  Two kept boxes per lane and vote, the kept rows' L2 prefetch moved off the settle
+//           warp, and a two-chain re-score in the gather changed nothing measurable either (31 us).)
 //   gather  kept rows are staged in shared memory, one thread per (row, group) recomputes
 //           nms.py:76-96 (group maxima with first-index argmax), one per (row, coordinate) emits the
 //           xyxy box and the corners, optionally mapped back to source coordinates
