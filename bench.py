@@ -456,12 +456,15 @@ def device_inputs_e2e(ranks, cfg, B, dev, Ke):
     cnt_host = [torch.empty((B,), dtype=torch.int32, pin_memory=True) for p in plans]
     copied = [torch.cuda.Event() for _ in plans]
 
+    copy_stream = torch.cuda.Stream(dev)     # D2H on its own stream: K2 of the next batch does not queue behind it
+
     def step():
         slot, out, counts = pipe.submit(cfg["conf"], cfg["iou"])
-        with torch.cuda.stream(pipe.s_nms):
+        copy_stream.wait_event(pipe.done[slot])
+        with torch.cuda.stream(copy_stream):
             cnt_host[slot].copy_(counts, non_blocking=True)
             out_host[slot].copy_(out, non_blocking=True)
-            copied[slot].record(pipe.s_nms)
+            copied[slot].record(copy_stream)
         return slot
 
     pipe.start()
