@@ -10,7 +10,8 @@
  *                               (+ torchvision.ops.nms, call site nms.py:121,
  *                                + xywh2xyxy nms.py:21-28)
  *   lp_detect_decode_f32     <- yolov6/models/effidehead.py:247-301
- *                               Detect.forward eval tail (after the convs)
+ *                               Detect.forward eval tail (after the convs);
+ *                               lp_detect_decode_half_scores_f32: the same under model.half()
  *   lp_generate_anchors_f32  <- yolov6/assigners/anchor_generator.py:11-31
  *   lp_dist2bbox_f32         <- yolov6/utils/general.py:29-40
  *   lp_dist2cor_f32          <- yolov6/utils/general.py:51-66
@@ -189,6 +190,16 @@ LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_str
  * materialised. */
 LP_API int lp_detect_decode_f32(const lp_level_t* levels_host, int n_levels, int B, float* out, lp_stream_t stream,
         const lp_opts_t* opts);
+
+/*
+ * The same for a model.half() forward (inferer.py:46-50): the caller upcasts the half conv outputs (exact)
+ * and every class score is rounded to the nearest IEEE half before it is stored as fp32 -- which is what the
+ * reference's head tensor holds in that mode: torch.sigmoid on half tensors rounds once, and torch.cat
+ * promotes the result to fp32 together with the box / corner columns, which the reference computes in
+ * fp32 even then because its anchor points are fp32 (effidehead.py:251-258, 283-301).
+ */
+LP_API int lp_detect_decode_half_scores_f32(const lp_level_t* levels_host, int n_levels, int B, float* out,
+                                            lp_stream_t stream, const lp_opts_t* opts);
 
 /*
  * Fused head tail + NMS: raw per-level conv outputs -> detections, without materialising the

@@ -78,9 +78,12 @@ def sigmoid(x):
 CLS_NAMES = ("pro", "alp", "ad0", "ad1", "ad2", "ad3", "ad4", "ad5")
 
 
-def detect_decode(levels, strides):
+def detect_decode(levels, strides, half_scores=False):
     """Eval tail of ``Detect.forward``, ``yolov6/models/effidehead.py:247-301``
-    (``use_dfl=False``): everything after the prediction convs.
+    (``use_dfl=False``): everything after the prediction convs.  ``half_scores``: the ``model.half()``
+    forward -- level tensors are halves (upcast exactly here), ``torch.sigmoid`` rounds every score to
+    half (:251-258) and ``torch.cat`` promotes it to fp32 with the geometry columns, which are computed
+    in fp32 because the anchor points are fp32 (:283-301).
 
     levels: list (per FPN level) of dicts with raw conv outputs, NCHW fp32:
     ``pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w] reg[B,4,h,w] cor[B,8,h,w]``.
@@ -91,13 +94,15 @@ def detect_decode(levels, strides):
     B = levels[0]["reg"].shape[0]
 
     def flat(name):  # effidehead.py:260-280  reshape [B,C,hw] -> cat levels -> permute
-        return np.concatenate([lv[name].reshape(B, lv[name].shape[1], -1) for lv in levels], -1).transpose(0, 2, 1)
+        return np.concatenate([np.asarray(lv[name], f32).reshape(B, lv[name].shape[1], -1) for lv in levels], -1).transpose(0, 2, 1)
 
     box = dist2bbox(flat("reg"), ap[None], "xywh")          # :283
     cor = dist2cor(flat("cor"), ap[None])                     # :284
     box = (box * st[None]).astype(f32)                        # :285
     cor = (cor * st[None]).astype(f32)                        # :286
     cls = [sigmoid(flat(n)) for n in CLS_NAMES]               # :251-258
+    if half_scores:
+        cls = [c.astype(np.float16).astype(f32) for c in cls]
     ones = np.ones((B, box.shape[1], 1), f32)                 # :290
     return np.concatenate([box, ones, cor] + cls, -1).astype(f32)   # :287-301
 

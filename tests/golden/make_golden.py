@@ -194,6 +194,36 @@ def make_decode():
         print("   A", out.shape[1], "counts", counts.tolist())
 
 
+def make_decode_half():
+    """The reference's model.half() forward (inferer.py:46-50) on the CPU: the head AND its inputs are
+    halves, the head tensor comes out fp32 (fp32 anchors promote the geometry, torch.cat promotes the
+    half sigmoids).  Stored: the half prediction-conv outputs (hooks), the head tensor, the NMS rows."""
+    head = build_head(rerandomise=True).half()
+    B, H, W = 2, 96, 160
+    feats = [torch.rand(B, c, H // s, W // s).half() for c, s in zip((64, 128, 256), (8, 16, 32))]
+    raw = [dict() for _ in range(3)]
+    hooks = []
+    for n in [n + "_preds" for n in CLS] + ["reg_preds", "cor_preds"]:
+        for lvl, conv in enumerate(getattr(head, n)):
+            hooks.append(conv.register_forward_hook(
+                lambda m, i, o, lvl=lvl, n=n: raw[lvl].__setitem__(n[:3], o.detach().clone())))
+    with torch.no_grad():
+        out = head([f.clone() for f in feats])
+    for h in hooks:
+        h.remove()
+    assert out.dtype == torch.float32 and all(v.dtype == torch.float16 for lv in raw for v in lv.values())
+    arrays = {}
+    for lvl in range(3):
+        for k, v in raw[lvl].items():
+            arrays[f"l{lvl}_{k}"] = v.numpy()
+    conf = 0.02
+    rows = run_ref_nms(out, conf, 0.45, 300, chunk=B)
+    counts, flat = pack_rows(rows)
+    save("decode_half_96x160", out=out.numpy(), conf=np.array(conf), iou=np.array(0.45), max_det=np.array(300),
+         counts=counts, rows=flat, hw=np.array([H, W]), **arrays)
+    print("   A", out.shape[1], "counts", counts.tolist())
+
+
 # ----------------------------------------------------------------- geometry + rescale KATs
 def make_geometry():
     g = torch.Generator().manual_seed(5)
@@ -366,6 +396,6 @@ def make_maxnms():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets", "iou_band", "maxnms"]
+    which = sys.argv[1:] or ["seeded", "edges", "decode", "geometry", "rescale", "txt", "eval", "targets", "iou_band", "maxnms", "decode_half"]
     for w in which:
         globals()["make_" + w]()

@@ -21,7 +21,7 @@ DEV = "cuda:0"
 
 SEEDED = golden_names("nms_cfg") + golden_names("nms_eval")
 EDGES = golden_names("nms_edge_")
-DECODE = golden_names("decode_")
+DECODE = [n for n in golden_names("decode_") if "half" not in n]
 
 
 def _knobs(g):
@@ -267,6 +267,32 @@ def test_decode_goldens(name):
     # stage-wise protocol: feed the GPU-decoded tensor to both NMS implementations
     conf, iou, max_det = _knobs(g)
     _check_against_oracle(torch.from_numpy(got), conf, iou, max_det, name + " decode->nms")
+
+
+def test_decode_half_mode_golden():
+    """The reference's model.half() forward (golden made by running the unmodified Detect in half on the
+    CPU, tests/golden/make_golden.py make_decode_half): half conv outputs in, fp32 head tensor out whose
+    class scores are sigmoids rounded to half.  lp_detect_decode_half_scores_f32: geometry columns
+    bit-exact; scores equal to the reference's except where the 1e-5 sigmoid difference straddles a
+    half rounding boundary (then one half ulp apart); then the stage-wise NMS protocol."""
+    g = golden("decode_half_96x160")
+    want = g["out"]
+    levels = _levels(g, DEV)
+    assert all(v.dtype == torch.float16 for lv in levels for v in lv.values())
+    got = lp.detect_decode(levels, (8, 16, 32), half_scores=True)
+    assert got.dtype == torch.float32
+    got = got.cpu().numpy()
+    assert np.array_equal(got[..., :13].view(np.uint32), want[..., :13].view(np.uint32)), "box/obj/corner columns"
+    sc, ws = got[..., 13:], want[..., 13:]
+    assert np.array_equal(sc, sc.astype(np.float16).astype(np.float32)), "scores are not half-representable"
+    assert (sc == ws).mean() >= 0.99
+    np.testing.assert_allclose(sc, ws, rtol=2.0 ** -10, atol=0)          # at most one half ulp
+    conf, iou, max_det = _knobs(g)
+    _check_against_oracle(torch.from_numpy(got), conf, iou, max_det, "half decode->nms")
+    # ... and the plain entry on the same (upcast) tensors differs from it by the rounding only
+    plain = lp.detect_decode(levels, (8, 16, 32)).cpu().numpy()
+    assert np.array_equal(plain[..., :13], got[..., :13])
+    assert np.array_equal(plain[..., 13:].astype(np.float16).astype(np.float32), sc)
 
 
 def test_decode_full_size_vs_oracle():

@@ -61,6 +61,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_debug_sigmoid_f32": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p]),
     "lp_detect_decode_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_detect_decode_half_scores_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_void_p, c_void_p, POINTER(LpOpts)]),
     "lp_detect_postprocess_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                           c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(LpOpts)]),
     "lp_detect_pipelined_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,

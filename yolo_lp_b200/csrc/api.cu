@@ -435,8 +435,8 @@ static int build_levels(const lp_level_t* levels, int n_levels, int B, DecodeLev
     return LP_OK;
 }
 
-LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream,
-                                const lp_opts_t* opts) {
+static int detect_decode(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream,
+                         const lp_opts_t* opts, bool half_scores) {
     if (!out) return LP_E_NULL;
     if (!aligned(out, 8)) return LP_E_ALIGN;
     const Opts o = resolve(opts);
@@ -450,11 +450,24 @@ LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, f
     p.tiles_per_image = tiles;
     p.n_tiles = tiles * B;
     p.bulk_in = bulk ? 1 : 0;
+    p.half_scores = half_scores ? 1 : 0;
     p.out = out;
     p.timing = o.timing;
     DecodeMaps maps;
     if (bulk && o.tma && aligned(out, 16) && build_decode_maps(p.lv, n_levels, B, maps)) p.bulk_in = 2;
     return (int)launch_decode(p, p.bulk_in == 2 ? &maps : nullptr, num_sms_cached(), static_cast<cudaStream_t>(stream));
+}
+
+LP_API int lp_detect_decode_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream,
+                                const lp_opts_t* opts) {
+    return detect_decode(levels, n_levels, B, out, stream, opts, false);
+}
+// The head tensor of the reference's model.half() forward from the (exactly upcast) half conv outputs: box /
+// obj / corner columns as above -- the reference computes them in fp32 too, its anchors being fp32 -- and
+// every class score rounded to the nearest IEEE half (torch.sigmoid on a half tensor) before it is stored.
+LP_API int lp_detect_decode_half_scores_f32(const lp_level_t* levels, int n_levels, int B, float* out, lp_stream_t stream,
+                                            const lp_opts_t* opts) {
+    return detect_decode(levels, n_levels, B, out, stream, opts, true);
 }
 
 // Everything the fused entries can reject (apart from the fp16 shape rule, which needs the tensor

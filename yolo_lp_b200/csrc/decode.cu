@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(const DecodePara
         if (tid == 0) bulk_wait_read1();
         __syncthreads();                  // ... and everybody else's copies
 
-        transpose_tile(stage, outt, t, lv, warp, lane);
+        transpose_tile(stage, outt, t, lv, warp, lane, p.half_scores != 0);
         fence_proxy_async_smem();  // generic-proxy writes of outt -> visible to the bulk store
         __syncthreads();           // also releases this stage for the copies queued next iteration
 

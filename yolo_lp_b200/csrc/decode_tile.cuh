@@ -1,6 +1,8 @@
 // Shared by the two decode kernels (decode.cu: LSU loads, decode_tma.cu: TMA loads + warp
 // specialisation): the out-tile geometry, the bulk-store PTX and the per-tile transposition.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "level_tiles.cuh"
 
 namespace lp {
@@ -18,9 +20,17 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// A class score as the head tensor holds it.  half_scores: rounded to the nearest half and widened again --
+// what the reference's model.half() forward stores (torch.sigmoid of a half tensor computes in fp32 and
+// rounds once; torch.cat with the fp32 geometry columns then promotes it, effidehead.py:251-258,288-301).
+__device__ __forceinline__ float class_score(float logit, bool half_scores) {
+    const float s = sigmoid_f32(logit);
+    return half_scores ? __half2float(__float2half_rn(s)) : s;
+}
+
 // One staged tile (channel-major, 32 positions per channel row) -> finished rows in `outt`.
 __device__ __forceinline__ void transpose_tile(const float* stage, float* outt, const TileInfo& t, const DecodeLevel& lv,
-                                               int warp, int lane) {
+                                               int warp, int lane, bool half_scores) {
     // class columns: lanes along positions (conflict-free stage reads), sigmoid, transposed write
     // Two adjacent columns per lane and one 64-bit store: with the packed 290-word row pitch a
     // 32-bit store per lane is a 2-way bank conflict (290 = 2 mod 32), a 64-bit one is conflict-free
@@ -30,11 +40,11 @@ __device__ __forceinline__ void transpose_tile(const float* stage, float* outt, 
 #pragma unroll 4
         for (int col = 14 + 2 * warp; col < ROW; col += 2 * DEC_WARPS) {
             float2 v;
-            v.x = sigmoid_f32(stage[col * DEC_TILE + lane]);
-            v.y = sigmoid_f32(stage[(col + 1) * DEC_TILE + lane]);
+            v.x = class_score(stage[col * DEC_TILE + lane], half_scores);
+            v.y = class_score(stage[(col + 1) * DEC_TILE + lane], half_scores);
             *reinterpret_cast<float2*>(orow + col) = v;
         }
-        if (warp == 0) orow[13] = sigmoid_f32(stage[13 * DEC_TILE + lane]);
+        if (warp == 0) orow[13] = class_score(stage[13 * DEC_TILE + lane], half_scores);
     }
     // box / objectness / corner columns: one thread per position
     if (warp == DEC_WARPS - 1 && lane < t.n) {

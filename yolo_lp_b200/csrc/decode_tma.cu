@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) decode_tma_kernel(const DecodeP
             LP_PF(0);
             mbar_wait_warp(&full[s], (it / DT_STAGES) & 1, lane);
             LP_PF(1);
-            transpose_tile(stage, outt, t, lv, warp, lane);
+            transpose_tile(stage, outt, t, lv, warp, lane, p.half_scores != 0);
             fence_proxy_async_smem();   // generic-proxy writes of outt -> visible to the bulk store
             LP_PF(2);
             tile_done_arrive(it);       // non-blocking; the release warp passes the tile on

@@ -40,6 +40,7 @@ struct DecodeParams {
     int tiles_per_image;
     int n_tiles;      // B * tiles_per_image
     int bulk_in;      // 0: 4-byte cp.async (unaligned planes), 1: 16-byte cp.async, 2: 3-D TMA boxes (DecodeMaps)
+    int half_scores;  // round every class score to the nearest IEEE half (the reference's model.half() head tensor)
     float* out;
     long long* timing;  // debug only (-DLP_DEC_PROFILE builds): per-CTA cycle sums, see decode_tma.cu
 };

@@ -132,8 +132,10 @@ class DecodePlan(_LevelTable):
     """Validated, pointer-resolved launch of the decode kernel for a fixed set of level tensors
     (e.g. the static output buffers of a CUDA-graphed head).  ``run()`` is a single C call."""
 
-    def __init__(self, levels, strides=(8, 16, 32), out: torch.Tensor | None = None):
+    def __init__(self, levels, strides=(8, 16, 32), out: torch.Tensor | None = None, half_scores: bool = False):
         super().__init__(levels, strides)
+        # half_scores: class scores rounded to half like the reference's model.half() head tensor
+        self._entry = "lp_detect_decode_half_scores_f32" if half_scores else "lp_detect_decode_f32"
         B, A = self.B, self.A
         if out is None:
             out = torch.empty((B, A, ROW), dtype=torch.float32, device=self.device)
@@ -144,8 +146,7 @@ class DecodePlan(_LevelTable):
 
     def run(self) -> torch.Tensor:
         with torch.cuda.device(self.device):
-            _abi.call("lp_detect_decode_f32", self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device),
-                      opts=self.opts)
+            _abi.call(self._entry, self.arr, self.n, self.B, self.out.data_ptr(), _stream(self.device), opts=self.opts)
         return self.out
 
 
@@ -273,14 +274,16 @@ def detect_postprocess(levels, strides=(8, 16, 32), conf_thres=0.25, iou_thres=0
     return [out[b, :k] for b, k in enumerate(counts.cpu().tolist())]
 
 
-def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None) -> torch.Tensor:
+def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None, half_scores: bool = False) -> torch.Tensor:
     """Eval tail of ``Detect.forward`` (effidehead.py:247-301, ``use_dfl=False``).
+    ``half_scores``: the ``model.half()`` variant -- class scores rounded to the nearest half (fp16 level
+    tensors are upcast exactly; the result is fp32 like the reference's, see :func:`detect_forward_eval`).
 
     ``levels``: per FPN level a dict of the raw prediction-conv outputs (NCHW, CUDA fp32):
     ``pro[B,31,h,w] alp[B,24,h,w] ad0..ad5[B,37,h,w] reg[B,4,h,w] cor[B,8,h,w]``.
     Returns the head tensor ``[B, A, 290]``.
     """
-    return DecodePlan(levels, strides, out).run()
+    return DecodePlan(levels, strides, out, half_scores).run()
 
 
 _PRED_ATTRS = tuple(n + "_preds" for n in CLS_NAMES)
@@ -305,9 +308,9 @@ def detect_forward_eval(detect, x):
     # model.half() (inferer.py:46-50): the reference's head tensor is fp32 even then -- its anchors are
     # fp32, so dist2bbox / dist2cor promote (general.py:29-66) and torch.cat promotes the half sigmoids
     # with them (effidehead.py:288-301).  The decode upcasts the half conv outputs exactly and computes
-    # in fp32, which IS the reference's arithmetic for the box / corner columns; the class columns are
-    # fp32 sigmoids where the reference's are sigmoids rounded to half.
-    return detect_decode(levels, [float(s) for s in detect.stride])
+    # in fp32, which IS the reference's arithmetic for the box / corner columns, and rounds the class
+    # scores to half as torch.sigmoid on a half tensor does (lp_detect_decode_half_scores_f32).
+    return detect_decode(levels, [float(s) for s in detect.stride], half_scores=x[0].dtype == torch.float16)
 
 
 def detect_forward_nms(detect, x, conf_thres=0.25, iou_thres=0.45, max_det=300):
