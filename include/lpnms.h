@@ -237,6 +237,9 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, 
  * results are bit for bit those of the f32 entries on the upcast tensors.  TMA kernel only: returns
  * LP_E_ARG unless every level has h*w % 8 == 0 and 16-byte aligned tensors -- upcast such inputs and
  * call the f32 entry.  K2 is shared: use lp_detect_suppress_f32 after lp_detect_filter_f16.
+ * (Scores are NOT rounded to half here: these entries equal lp_detect_decode_f32 + lp_nms_f32 on the
+ * upcast tensors, not lp_detect_decode_half_scores_f32 + lp_nms_f32 -- the fused call has no counterpart
+ * in the reference, so there is no half-mode head tensor of the reference's to match.)
  */
 LP_API int lp_detect_postprocess_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
                                      double iou_thres, int max_det, int max_nms, void* workspace,
