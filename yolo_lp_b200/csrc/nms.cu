@@ -40,7 +40,11 @@
 //           warp, and a two-chain re-score in the gather changed nothing measurable either (31 us); nor did
 //           ONE barrier per step -- every warp settling the chunk redundantly, the previous step's kept
 //           members tested straight from the window: the settle then takes 1.4 thousand cycles in each
-//           of the 32 warps instead of 0.7 in warp 0 plus a barrier, 2.9 against 2.7 thousand per step.)
+//           of the 32 warps instead of 0.7 in warp 0 plus a barrier, 2.9 against 2.7 thousand per step.
+//           A gather with one WARP per kept row -- ten coalesced loads per lane straight from the head
+//           tensor, group maximum / first argmax by REDUX + ballots, no staging, no barrier -- took 14.5
+//           thousand cycles where the staged thread-per-(row, group) re-score takes 10.9: ~200 warp
+//           instructions per row against ~50.)
 //   gather  kept rows are staged in shared memory, one thread per (row, group) recomputes
 //           nms.py:76-96 (group maxima with first-index argmax), one per (row, coordinate) emits the
 //           xyxy box and the corners, optionally mapped back to source coordinates
