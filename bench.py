@@ -445,50 +445,53 @@ def h2d_ceiling(ranks, host_pred, dev_buf, reps):
 def device_inputs_e2e(ranks, cfg, B, dev, Ke):
     """Production flow when the head runs on this GPU: raw level tensors are already in HBM, the
     fused path (KF + K2) turns them into detections and those go D2H into pinned memory -- the timed
-    region includes that copy and the wait for it, every step."""
+    region includes that copy, every step, and the host takes every batch's detections in order.  A batch
+    takes ~150 us from its submission to its detections being visible on the host (queueing behind the
+    previous batches + KF 56 + K2 33 + D2H 26 us), so four are kept in flight (the host waits for batch
+    i - 3 before it submits batch i + 1; tools/device_inputs_probe.py: 142 / 79 / 53 us per step with 2 / 3
+    / 4 in flight, 52 us without any host wait), each submitted by ONE native call
+    (lp_detect_pipelined_to_host_f32)."""
     import torch
     from yolo_lp_b200 import synth
     from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+    DEPTH = 4
     levels = synth.synth_levels(B, cfg["img"], cfg["img"], dev, seed=cfg["seed"])
-    plans = [PostprocessPlan(levels, (8, 16, 32), cfg["max_det"]) for _ in range(2)]
+    plans = [PostprocessPlan(levels, (8, 16, 32), cfg["max_det"]) for _ in range(DEPTH)]
     pipe = PostprocessPipeline(plans)
     out_host = [torch.empty(tuple(p.out.shape), dtype=torch.float32, pin_memory=True) for p in plans]
     cnt_host = [torch.empty((B,), dtype=torch.int32, pin_memory=True) for p in plans]
     copied = [torch.cuda.Event() for _ in plans]
-
     copy_stream = torch.cuda.Stream(dev)     # D2H on its own stream: K2 of the next batch does not queue behind it
 
-    def step():
-        slot, out, counts = pipe.submit(cfg["conf"], cfg["iou"])
-        copy_stream.wait_event(pipe.done[slot])
-        with torch.cuda.stream(copy_stream):
-            cnt_host[slot].copy_(counts, non_blocking=True)
-            out_host[slot].copy_(out, non_blocking=True)
-            copied[slot].record(copy_stream)
-        return slot
+    def run(n):
+        """n steps; a slot is resubmitted only after the host has taken its previous batch."""
+        inflight, dets = [], 0
+        pipe.start()
+        for _ in range(n):
+            if len(inflight) == DEPTH - 1:
+                slot = inflight.pop(0)
+                copied[slot].synchronize()
+                dets += int(cnt_host[slot][0])             # the host reads the batch it waited for
+            slot = pipe.n % DEPTH
+            inflight.append(pipe.submit_to_host(cfg["conf"], cfg["iou"], out_host[slot], cnt_host[slot], copy_stream, copied[slot]))
+        for slot in inflight:
+            copied[slot].synchronize()
+        pipe.finish()
+        return dets
 
-    pipe.start()
-    for _ in range(4):
-        step()
-    pipe.finish()
+    run(2 * DEPTH)
+    torch.cuda.synchronize(dev)
     ranks.barrier()
     t0 = time.perf_counter()
-    pipe.start()
-    prev = None
-    for _ in range(Ke):
-        slot = step()
-        if prev is not None:
-            copied[prev].synchronize()      # the host consumes batch i-1 while batch i is in flight
-        prev = slot
-    copied[prev].synchronize()
-    pipe.finish()
+    run(Ke)
     torch.cuda.synchronize(dev)
     ms = ranks.max((time.perf_counter() - t0) * 1e3) / Ke
     d2h = out_host[0].numel() * 4 + cnt_host[0].numel() * 4
     return {"value": ranks.world * B / ms * 1e3, "unit": UNIT, "ms_per_step": ms, "steps": Ke, "h2d_bytes_per_step": 0,
-            "d2h_bytes_per_step": d2h, "detections_per_image": float(cnt_host[prev].float().mean()),
-            "api": "PostprocessPipeline.submit (lp_detect_pipelined_f32) on device-resident level tensors + pinned D2H of "
-                   "out[B,max_det,28] and counts[B], host waits for every batch"}
+            "d2h_bytes_per_step": d2h, "detections_per_image": float(cnt_host[0].float().mean()), "batches_in_flight": DEPTH,
+            "api": "PostprocessPipeline.submit_to_host (lp_detect_pipelined_to_host_f32: KF + K2 + pinned D2H of out[B,max_det,28] "
+                   "and counts[B] in one native call) on device-resident level tensors; the host waits for every batch, in "
+                   "order, three steps behind the submission"}
 
 
 # --------------------------------------------------------------------------------------------- side rows

@@ -232,6 +232,29 @@ LP_API int lp_detect_pipelined_f32(const lp_level_t* levels_host, int n_levels, 
         const lp_opts_t* opts);
 
 /*
+ * lp_detect_pipelined_f32 followed by the copy of the step's results to pinned HOST memory, in one call --
+ * the production flow when the head runs on this GPU: level tensors resident in HBM, detections wanted on
+ * the host (Inferer.infer's per-image loop, inferer.py:100-120).  After K2, copy_stream waits for done_event
+ * (required), copies counts[B] -> counts_host_pinned and out[B,max_det,28] -> out_host_pinned with
+ * cudaMemcpyAsync, and records copied_event (cudaEvent_t, required): wait for it, then read the rows of
+ * image b as out_host_pinned[b, :counts_host_pinned[b]].  No kept_anchor / timing events here.
+ */
+LP_API int lp_detect_pipelined_to_host_f32(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                           double iou_thres, int max_det, int max_nms, void* workspace,
+                                           size_t workspace_bytes, float* out, int* counts, const float* rescale,
+                                           int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
+                                           void* workspace_free_event, void* filtered_event, void* done_event,
+                                           float* out_host_pinned, int* counts_host_pinned, lp_stream_t copy_stream,
+                                           void* copied_event, const lp_opts_t* opts);
+LP_API int lp_detect_pipelined_to_host_f16(const lp_level_t* levels_host, int n_levels, int B, double conf_thres,
+                                           double iou_thres, int max_det, int max_nms, void* workspace,
+                                           size_t workspace_bytes, float* out, int* counts, const float* rescale,
+                                           int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
+                                           void* workspace_free_event, void* filtered_event, void* done_event,
+                                           float* out_host_pinned, int* counts_host_pinned, lp_stream_t copy_stream,
+                                           void* copied_event, const lp_opts_t* opts);
+
+/*
  * The fused path on fp16 level tensors (model.half(): the prediction convs emit halves).  The
  * pointers in lp_level_t then address IEEE halves; every value is upcast exactly on load, so the
  * results are bit for bit those of the f32 entries on the upcast tensors.  TMA kernel only: returns

@@ -925,3 +925,40 @@ def test_long_suppression_chain_takes_the_sequential_pass(n, shift):
     assert len(widx[0]) > n // 4
     assert np.array_equal(idx[0].cpu().numpy(), widx[0])
     assert_rows_equal(rows[0].cpu().numpy(), want[0], "chain")
+
+
+@pytest.mark.parametrize("half", [False, True])
+def test_fused_pipeline_to_host_entry(half):
+    """lp_detect_pipelined_to_host_f32 / _f16: KF + K2 + the D2H copy of the step's detections in one native
+    call; what lands in the pinned host buffers equals the serial entry's result, step after step (three
+    slots' worth, so every workspace is re-armed)."""
+    from yolo_lp_b200.head import PostprocessPlan, PostprocessPipeline
+    B = 6
+    levels = synth.synth_levels(B, 640, 640, DEV, seed=21)
+    if half:
+        levels = [{k: v.half() for k, v in lv.items()} for lv in levels]
+    ref = PostprocessPlan(levels, (8, 16, 32), 300)
+    ref_out, ref_counts = (t.cpu() for t in ref.run(0.25, 0.45))
+    plans = [PostprocessPlan(levels, (8, 16, 32), 300) for _ in range(2)]
+    assert plans[0].half == half
+    pipe = PostprocessPipeline(plans)
+    copy_stream = torch.cuda.Stream(DEV)
+    outs = [torch.full((B, 300, 28), float("nan")).pin_memory() for _ in plans]
+    cnts = [torch.full((B,), -1, dtype=torch.int32).pin_memory() for _ in plans]
+    evs = [torch.cuda.Event() for _ in plans]
+    pipe.start()
+    for step in range(6):
+        slot = pipe.n % 2
+        if step >= 2:
+            evs[slot].synchronize()          # the host takes the slot's previous batch before it is reused
+        outs[slot].fill_(float("nan"))
+        got = pipe.submit_to_host(0.25, 0.45, outs[slot], cnts[slot], copy_stream, evs[slot])
+        assert got == slot
+    for slot in range(2):
+        evs[slot].synchronize()
+        assert torch.equal(cnts[slot], ref_counts) and int(ref_counts.sum()) > 0
+        for b, k in enumerate(ref_counts.tolist()):
+            assert torch.equal(outs[slot][b, :k], ref_out[b, :k]), f"slot {slot} image {b}"
+    pipe.finish()
+    with pytest.raises(ValueError):
+        pipe.submit_to_host(0.25, 0.45, torch.empty((B, 300, 28)), cnts[0], copy_stream, evs[0])   # not pinned

@@ -67,6 +67,12 @@ SIGNATURES = {
     "lp_detect_pipelined_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
                                         c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_detect_pipelined_to_host_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
+                                                c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
+    "lp_detect_pipelined_to_host_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,
+                                                c_size_t, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(LpOpts)]),
     "lp_detect_workspace_bytes": (c_int, [c_int, c_int, c_int, POINTER(c_size_t)]),
     "lp_detect_filter_f32": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_int, c_void_p, c_size_t, c_void_p, POINTER(LpOpts)]),
     "lp_detect_postprocess_f16": (c_int, [POINTER(LpLevel), c_int, c_int, c_double, c_double, c_int, c_int, c_void_p,

@@ -676,6 +676,48 @@ LP_API int lp_detect_pipelined_f16(const lp_level_t* levels, int n_levels, int B
                             filtered_event, done_event, time_begin_event, time_end_event, opts, true);
 }
 
+// lp_detect_pipelined_* plus the copy of the step's results into pinned HOST buffers: the production flow
+// when the head runs on this GPU (level tensors in HBM, detections wanted on the host) as ONE call per step.
+static int detect_pipelined_to_host(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                    int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out, int* counts,
+                                    const float* rescale, int do_round, lp_stream_t filter_stream, lp_stream_t nms_stream,
+                                    void* workspace_free_event, void* filtered_event, void* done_event, float* out_host,
+                                    int* counts_host, lp_stream_t copy_stream, void* copied_event, const lp_opts_t* opts,
+                                    bool half) {
+    if (!done_event || !out_host || !counts_host || !copied_event) return LP_E_NULL;
+    int rc = detect_pipelined(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes, out,
+                              counts, nullptr, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
+                              filtered_event, done_event, nullptr, nullptr, opts, half);
+    if (rc != LP_OK) return rc;
+    cudaStream_t sc = static_cast<cudaStream_t>(copy_stream);
+    cudaError_t e = cudaStreamWaitEvent(sc, static_cast<cudaEvent_t>(done_event), 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts_host, counts, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out_host, out, sizeof(float) * LP_OUT * (size_t)B * (size_t)max_det, cudaMemcpyDeviceToHost, sc);
+    if (e == cudaSuccess) e = cudaEventRecord(static_cast<cudaEvent_t>(copied_event), sc);
+    return (int)e;
+}
+LP_API int lp_detect_pipelined_to_host_f32(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                           int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                           int* counts, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                           lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                           void* done_event, float* out_host, int* counts_host, lp_stream_t copy_stream,
+                                           void* copied_event, const lp_opts_t* opts) {
+    return detect_pipelined_to_host(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes,
+                                    out, counts, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
+                                    filtered_event, done_event, out_host, counts_host, copy_stream, copied_event, opts, false);
+}
+LP_API int lp_detect_pipelined_to_host_f16(const lp_level_t* levels, int n_levels, int B, double conf_thres, double iou_thres,
+                                           int max_det, int max_nms, void* workspace, size_t workspace_bytes, float* out,
+                                           int* counts, const float* rescale, int do_round, lp_stream_t filter_stream,
+                                           lp_stream_t nms_stream, void* workspace_free_event, void* filtered_event,
+                                           void* done_event, float* out_host, int* counts_host, lp_stream_t copy_stream,
+                                           void* copied_event, const lp_opts_t* opts) {
+    return detect_pipelined_to_host(levels, n_levels, B, conf_thres, iou_thres, max_det, max_nms, workspace, workspace_bytes,
+                                    out, counts, rescale, do_round, filter_stream, nms_stream, workspace_free_event,
+                                    filtered_event, done_event, out_host, counts_host, copy_stream, copied_event, opts, true);
+}
+
 LP_API int lp_debug_sigmoid_f32(const float* in, long long n, float* out, lp_stream_t stream) {
     if (!in || !out) return LP_E_NULL;
     if (n < 0) return LP_E_SIZE;

@@ -251,6 +251,29 @@ class PostprocessPipeline:
         self.n += 1
         return slot, plan.out, plan.counts
 
+    def submit_to_host(self, conf_thres, iou_thres, out_host: torch.Tensor, counts_host: torch.Tensor,
+                       copy_stream: torch.cuda.Stream, copied: torch.cuda.Event):
+        """:meth:`submit` plus the D2H copy of the step's ``out`` / ``counts`` into the pinned host tensors on
+        ``copy_stream``, all in ONE native call (``lp_detect_pipelined_to_host_f32``); ``copied`` fires when
+        the host may read them.  Returns the slot."""
+        slot = self.n % len(self.plans)
+        plan = self.plans[slot]
+        if not (out_host.is_pinned() and counts_host.is_pinned()) or out_host.dtype != torch.float32 or \
+                counts_host.dtype != torch.int32 or tuple(out_host.shape) != tuple(plan.out.shape) or counts_host.numel() != plan.B:
+            raise ValueError("out_host / counts_host must be pinned fp32 [B,max_det,28] / int32 [B] tensors")
+        if copied.cuda_event == 0:       # torch creates the cudaEvent_t lazily, on the first record
+            copied.record(copy_stream)
+        s_filter = self.s_filters[self.n % len(self.s_filters)]
+        armed, plan.armed = plan.armed, False   # re-armed only once the whole step has been queued
+        _abi.call("lp_detect_pipelined_to_host" + plan._sfx, plan.arr, plan.n, plan.B, float(conf_thres), float(iou_thres),
+                  plan.max_det, plan.max_nms, plan.workspace.data_ptr(), plan.workspace.numel(), plan.out.data_ptr(),
+                  plan.counts.data_ptr(), None, 0, s_filter.cuda_stream, self.s_nms.cuda_stream,
+                  self.done[slot].cuda_event if armed else None, self.filtered[slot].cuda_event, self.done[slot].cuda_event,
+                  out_host.data_ptr(), counts_host.data_ptr(), copy_stream.cuda_stream, copied.cuda_event, opts=plan.opts)
+        plan.armed = True
+        self.n += 1
+        return slot
+
     def finish(self):
         cur = torch.cuda.current_stream(self.device)
         for sf in self.s_filters:
