@@ -294,7 +294,8 @@ def detect_postprocess(levels, strides=(8, 16, 32), conf_thres=0.25, iou_thres=0
     assert 0 <= iou_thres <= 1, f'iou_thres must be in 0.0 to 1.0, however {iou_thres} is provided.'
     plan = PostprocessPlan(levels, strides, max_det)
     out, counts = plan.run(conf_thres, iou_thres)
-    return [out[b, :k] for b, k in enumerate(counts.cpu().tolist())]
+    from .nms import rows_of
+    return rows_of(out, counts.cpu().tolist())
 
 
 def detect_decode(levels, strides=(8, 16, 32), out: torch.Tensor | None = None, half_scores: bool = False) -> torch.Tensor:

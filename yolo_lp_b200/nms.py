@@ -69,6 +69,17 @@ class NmsPlan:
         # candidate counters zeroed): only then may the next pipelined step skip its memset
         self.armed = False
         self.opts = None   # _abi.opts(...): per-call tuning / debug knobs (tests, tools); None = production
+        self._counts_host = None
+
+    def counts_to_host(self, counts: torch.Tensor | None = None) -> list:
+        """The call's one host sync: ``counts`` -> a pinned buffer -> Python ints (a pinned target keeps the
+        copy asynchronous and saves the pageable staging of ``.cpu()``)."""
+        counts = self.counts if counts is None else counts
+        if self._counts_host is None:
+            self._counts_host = torch.empty((self.B,), dtype=torch.int32, pin_memory=True)
+        self._counts_host.copy_(counts, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._counts_host.tolist()
 
     def run(self, pred: torch.Tensor, conf_thres: float, iou_thres: float, rescale: torch.Tensor | None = None,
             do_round: bool = False, out=None, counts=None):
@@ -236,6 +247,17 @@ class GraphedSteps:
         self.graph.replay()
 
 
+def rows_of(out: torch.Tensor, ks) -> list:
+    """``[out[b, :k] for b, k in enumerate(ks)]`` as views of the padded ``[B, max_det, 28]`` buffer, built
+    by ONE ``split_with_sizes`` instead of B Python indexing operations (which cost more host time than the
+    kernels for a 32-image batch)."""
+    B, M, W = out.shape
+    sizes = [0] * (2 * B)
+    sizes[0::2] = ks
+    sizes[1::2] = [M - k for k in ks]
+    return list(out.view(B * M, W).split_with_sizes(sizes)[0::2])
+
+
 _plans: dict = {}
 
 
@@ -285,11 +307,11 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     pred = _device_input(prediction)
     plan = _plan_for(B, A, int(max_det), pred.device)
     out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
-    _, counts = plan.run(pred, conf_thres, iou_thres, out=out)
-    ks = counts.cpu().tolist()  # the one host sync of the call
+    plan.run(pred, conf_thres, iou_thres, out=out)
+    ks = plan.counts_to_host()  # the one host sync of the call
     if pred.dtype == torch.float16:   # rows in the prediction's dtype, like the reference's torch.cat
         out = out.half()
-    return [out[b, :k] for b, k in enumerate(ks)]
+    return rows_of(out, ks)
 
 
 def non_max_suppression_with_index(prediction, conf_thres=0.25, iou_thres=0.45, max_det=300):
@@ -300,10 +322,10 @@ def non_max_suppression_with_index(prediction, conf_thres=0.25, iou_thres=0.45, 
     B, A, _ = pred.shape
     plan = _plan_for(B, A, int(max_det), pred.device, want_anchor=True)
     out = torch.empty((B, plan.max_det, OUT), dtype=torch.float32, device=pred.device)
-    _, counts = plan.run(pred, conf_thres, iou_thres, out=out)
-    ks = counts.cpu().tolist()
+    plan.run(pred, conf_thres, iou_thres, out=out)
+    ks = plan.counts_to_host()
     idx = plan.kept_anchor.clone()
-    return [out[b, :k] for b, k in enumerate(ks)], [idx[b, :k].long() for b, k in enumerate(ks)]
+    return rows_of(out, ks), [idx[b, :k].long() for b, k in enumerate(ks)]
 
 
 def xywh2xyxy(x):
