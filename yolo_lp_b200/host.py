@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from . import _abi
-from .nms import NmsPlan, OUT, ROW
+from .nms import NmsPlan, OUT, ROW, rows_of
 
 _CHUNK_BYTES = 48 << 20  # ~48 MiB per H2D chunk: long enough for full PCIe rate, short pipeline fill
 
@@ -75,7 +75,11 @@ class HostPipeline:
                 self.out_host.copy_(self.out_dev, non_blocking=True)
             self.compute_stream.synchronize()
         ks = self.counts_host.tolist()
-        return [self.out_host[b, :k].clone() for b, k in enumerate(ks)]
+        # the pinned buffer is reused by the next call: hand out copies -- ONE cat of the used rows and one
+        # split instead of B clones (which cost ~2 % of a PCIe-bound batch)
+        if sum(ks) == 0:
+            return [self.out_host.new_zeros((0, OUT)) for _ in ks]
+        return list(torch.cat(rows_of(self.out_host, ks)).split_with_sizes(ks))
 
 
 _pipes: dict = {}
