@@ -39,8 +39,12 @@
 // cycles a warp needs to issue eight UTMALDGs); the same with dedicated producer warps 70 us; this
 // kernel with maxima-only scanners and finisher-side argmax recovery 75 us (the finisher then holds the
 // slot ~2000 cycles longer, and five slots is all that fits); this kernel with four producer warps 68 us.
-// What limits it is the time a slot spends NOT loading (issue ~1000 + scan ~860 + hand-offs) against five
-// slots of 35 KB; what did help, mostly on dense tiles (150 -> 127 us), is mbar_wait_warp below.
+// A per-role clock profile of THIS kernel then showed that its steady state is already at K1's HBM pace
+// (a tile per 1256 cycles per CTA on 116 SMs, K1: 1220): the 0.81 of a launch timed alone is its ramp
+// (two producer lanes need ~2500 cycles to request the first five tiles) and its tail (a finisher's tile
+// takes ~6000 cycles from slot barrier to last row store, during which HBM idles at the end of the
+// launch) -- exactly what back-to-back launches on alternating streams overlap.  What did help, mostly
+// on dense tiles (150 -> 127 us), is mbar_wait_warp below.
 // Positions past the end of a level are zero-filled by the TMA unit and masked by `valid`.
 #include <type_traits>
 
