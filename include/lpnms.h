@@ -18,7 +18,9 @@
  *   lp_xywh2xyxy_f32         <- yolov6/utils/nms.py:21-28
  *   lp_rescale_f32           <- yolov6/core/inferer.py:203-228 (+ .round() :100)
  *   lp_rescale_batch_f32     <- same, one launch for a whole [B,max_det,28] batch
- *   lp_detect_postprocess_f32 <- effidehead.py:247-301 + nms.py:31-130 fused (no head tensor)
+ *   lp_detect_postprocess_f32 <- effidehead.py:247-301 + nms.py:31-130 fused (no head tensor);
+ *                               lp_detect_pipelined_to_host_f32: one pipelined step of it + the D2H copy
+ *                               of the detections (the post-model flow of Inferer.infer, inferer.py:82-120)
  *   lp_txt_records_f32 / lp_txt_lines_host <- yolov6/core/inferer.py:92-93,103-120 (--save-txt records)
  *   lp_eval_match_f32 / lp_eval_accumulate_host <- yolov6/core/evaler.py:153-283 (LP metric)
  *   lp_prepare_targets_f32   <- yolov6/core/evaler.py:119-127 (Evaler.predict label prep)
