@@ -13,4 +13,11 @@ against outputs of the reference itself, imported from ``/root/reference`` in
 the build container with torchvision 0.26.0 (CPU kernel); those outputs are
 committed under ``tests/golden/`` together with ``tests/golden/make_golden.py``
 that produced them.  ``tests/test_oracle_golden.py`` replays them.
+
+Three pieces: ``lp_oracle`` (numpy fp32 restatement, every function citing its reference lines),
+``torch_port`` (torch-CPU port with the real ``torchvision.ops.nms``) and ``stage_ref`` -- the recipe
+that stages the UNMODIFIED reference package byte for byte under ``oracle/_ref/`` (git-ignored, shipped
+to the GPU box with the snapshot), where it is the timed CPU arm of ``bench.py`` and the checker of the
+``-m gpu`` tests that run ``patch.install()`` on the real ``Detect`` / ``non_max_suppression`` /
+``Inferer.rescale``.
 """
